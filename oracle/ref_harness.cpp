@@ -1,0 +1,274 @@
+// ref_harness.cpp — C-ABI wrapper around the UNMODIFIED reference classes, compiled together with the
+// reference's own translation units where they lie under /root/reference (see oracle/Makefile).
+//
+// TEST INFRASTRUCTURE ONLY. Output goes to oracle/_ref/libchessai_ref.so. Only tests/, bench.py's
+// cpu_baseline / --impl reference leg and __graft_entry__.smoke() may load it; the product path never does.
+//
+// Everything here calls the reference's own code:
+//   network::Network::predictPosition        /root/reference/src/mcts_network/network.cpp:92-117
+//   network::Optimizer::optimize / dropout    network.cpp:223-292
+//   operator>> / operator<< (Network*&)       network.cpp:386-426
+//   game::operator>>(istream&, Board*&)       /root/reference/src/chess/game.cpp:343-370
+//   piece::Piece::code() and overrides        /root/reference/src/chess/piece.cpp:103-105,145-147,179-181,260-262
+//   network::load_training_case               /root/reference/src/main/network/make_cases.cpp:123-129
+//   decider::Decider::prediction              /root/reference/src/mcts_network/decider.cpp:31-61
+// Compiled with -fno-access-control so private members (predictPosition, _connections) are reachable
+// without touching the reference sources.
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "mcts_network/network.h"
+#include "mcts_network/decider.h"
+#include "chess/game.h"
+#include "chess/piece.h"
+#include "main/network/make_cases.h"
+#include "util/math_util.h"
+#include "util/string_util.h"
+
+namespace {
+
+// code k in [-9, 9] -> the piece line of the reference's board text format (game.cpp:372-379, piece.cpp:300-375)
+const char *piece_text(int k) {
+  switch (k) {
+    case 0: return "none none .";
+    case 1: return "king white false";
+    case 2: return "king white true";
+    case 3: return "queen white .";
+    case 4: return "rook white false";
+    case 5: return "rook white true";
+    case 6: return "knight white .";
+    case 7: return "bishop white .";
+    case 8: return "pawn white false";
+    case 9: return "pawn white true";
+    case -1: return "king black false";
+    case -2: return "king black true";
+    case -3: return "queen black .";
+    case -4: return "rook black false";
+    case -5: return "rook black true";
+    case -6: return "knight black .";
+    case -7: return "bishop black .";
+    case -8: return "pawn black false";
+    case -9: return "pawn black true";
+    default: return nullptr;
+  }
+}
+
+game::Board *board_from_codes(const int8_t *codes) {
+  std::stringstream ss;
+  ss << "8 8\n";
+  for (int i = 0; i < 64; ++i) {
+    const char *txt = piece_text(codes[i]);
+    if (txt == nullptr) return nullptr;
+    ss << i << " - " << txt << "\n";
+  }
+  auto *b = new game::Board(8, 8);
+  ss >> b;  // the reference's own parser
+  return b;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- network lifetime / IO -------------------------------------------------------------------------
+void *ref_net_load(const char *path) { return network::Network::loadFromFile(path); }
+
+void *ref_net_new(const int *dims, int n_dims) {
+  std::vector<int> d(dims, dims + n_dims);
+  return new network::Network(d);
+}
+
+// Network::randomNetwork(dims) — draws from the reference's own (default-seeded, per-TU) mt19937.
+void *ref_net_random(const int *dims, int n_dims) {
+  std::vector<int> d(dims, dims + n_dims);
+  return network::Network::randomNetwork(d);
+}
+
+void *ref_net_clone(void *net) { return static_cast<network::Network *>(net)->clone(); }
+
+void ref_net_free(void *net) { delete static_cast<network::Network *>(net); }
+
+int ref_net_num_layers(void *net) { return static_cast<network::Network *>(net)->_num_layers; }
+
+void ref_net_dims(void *net, int *out) {
+  auto *n = static_cast<network::Network *>(net);
+  for (int i = 0; i < n->_num_layers; ++i) out[i] = n->_dimensions[i];
+}
+
+long ref_net_num_weights(void *net) {
+  auto *n = static_cast<network::Network *>(net);
+  long c = 0;
+  for (int l = 0; l + 1 < n->_num_layers; ++l) c += (long) n->_dimensions[l] * n->_dimensions[l + 1];
+  return c;
+}
+
+// flat n,i,j order == line 3 of the dump format
+void ref_net_get_weights(void *net, double *out) {
+  auto *n = static_cast<network::Network *>(net);
+  long c = 0;
+  for (int l = 0; l + 1 < n->_num_layers; ++l)
+    for (int i = 0; i < n->_dimensions[l]; ++i)
+      for (int j = 0; j < n->_dimensions[l + 1]; ++j) out[c++] = n->_connections[l][i][j];
+}
+
+void ref_net_set_weights(void *net, const double *in) {
+  auto *n = static_cast<network::Network *>(net);
+  long c = 0;
+  for (int l = 0; l + 1 < n->_num_layers; ++l)
+    for (int i = 0; i < n->_dimensions[l]; ++i)
+      for (int j = 0; j < n->_dimensions[l + 1]; ++j) n->_connections[l][i][j] = in[c++];
+}
+
+// operator<< into a file; returns 0 on success
+int ref_net_dump(void *net, const char *path) {
+  auto *n = static_cast<network::Network *>(net);
+  std::ofstream out(path);
+  if (!out.is_open()) return 1;
+  out << n;
+  return 0;
+}
+
+// ---- encoder -----------------------------------------------------------------------------------------
+// Parses a training-case file with the reference's own loader and returns Piece::code() per square and the target.
+int ref_load_case(const char *path, double *codes_out, double *target_out) {
+  auto tc = network::load_training_case(path, false);
+  std::vector<piece::Piece *> pcs = tc.first->pieces();
+  for (int i = 0; i < 64; ++i) codes_out[i] = pcs[i]->code();
+  *target_out = tc.second;
+  delete tc.first;
+  return 0;
+}
+
+// code() of a board built from int8 codes through the text format (round trip of the encoder)
+int ref_codes_to_inputs(const int8_t *codes, double *inputs_out) {
+  game::Board *b = board_from_codes(codes);
+  if (b == nullptr) return 1;
+  std::vector<piece::Piece *> pcs = b->pieces();
+  for (int i = 0; i < 64; ++i) inputs_out[i] = pcs[i]->code();
+  delete b;
+  return 0;
+}
+
+// ---- forward -----------------------------------------------------------------------------------------
+int ref_predict_codes(void *net, const int8_t *codes, long n_boards, double *out) {
+  auto *n = static_cast<network::Network *>(net);
+  for (long b = 0; b < n_boards; ++b) {
+    game::Board *board = board_from_codes(codes + 64 * b);
+    if (board == nullptr) return 1;
+    out[b] = n->predictPosition(board);
+    delete board;
+  }
+  return 0;
+}
+
+// Timed forward over pre-built boards, `threads` host threads, one Network::clone() per thread over disjoint
+// shards (predictPosition is re-entrant, network.cpp:93-94). Returns seconds of wall time for the predict loop only.
+double ref_time_predict(void *net, const int8_t *codes, long n_boards, int threads, double *out) {
+  auto *n = static_cast<network::Network *>(net);
+  std::vector<game::Board *> boards(n_boards);
+  for (long b = 0; b < n_boards; ++b) boards[b] = board_from_codes(codes + 64 * b);
+  if (threads < 1) threads = 1;
+  std::vector<network::Network *> nets(threads);
+  for (int t = 0; t < threads; ++t) nets[t] = n->clone();
+  std::atomic<int> ready(0);
+  std::atomic<bool> go(false);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&, t] {
+      long lo = n_boards * t / threads, hi = n_boards * (t + 1) / threads;
+      ready.fetch_add(1);
+      while (!go.load()) {}
+      for (long b = lo; b < hi; ++b) out[b] = nets[t]->predictPosition(boards[b]);
+    });
+  while (ready.load() < threads) {}
+  auto t0 = std::chrono::steady_clock::now();
+  go.store(true);
+  for (auto &th : pool) th.join();
+  auto t1 = std::chrono::steady_clock::now();
+  for (auto *b : boards) delete b;
+  for (auto *c : nets) delete c;
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- training ----------------------------------------------------------------------------------------
+int ref_optimize_codes(void *net, const int8_t *codes, double target, double *lambda, double max_const, double rate) {
+  auto *n = static_cast<network::Network *>(net);
+  game::Board *board = board_from_codes(codes);
+  if (board == nullptr) return 1;
+  network::Optimizer::optimize(n, board, target, *lambda, max_const, rate);
+  delete board;
+  return 0;
+}
+
+// train.cpp:39-68 restated around the reference's own optimize/dropout for a fixed case order:
+// lambda reset + dropout when lambda leaves [1e-4, 10]. Returns the number of resets.
+int ref_train_sequence(void *net, const int8_t *codes, const double *targets, long n_cases, double *lambda) {
+  auto *n = static_cast<network::Network *>(net);
+  const double LAMBDA_MIN = 0.0001, LAMBDA_MAX = 10.0;
+  int resets = 0;
+  for (long c = 0; c < n_cases; ++c) {
+    game::Board *board = board_from_codes(codes + 64 * c);
+    if (board == nullptr) return -1;
+    network::Optimizer::optimize(n, board, targets[c], *lambda);
+    delete board;
+    if (*lambda < LAMBDA_MIN || LAMBDA_MAX < *lambda) {
+      *lambda = network::Optimizer::DEFAULT_INITIAL_LAMBDA;
+      network::Optimizer::dropout(n);
+      ++resets;
+    }
+  }
+  return resets;
+}
+
+double ref_time_train(void *net, const int8_t *codes, const double *targets, long n_cases, double *lambda) {
+  auto *n = static_cast<network::Network *>(net);
+  std::vector<game::Board *> boards(n_cases);
+  for (long b = 0; b < n_cases; ++b) boards[b] = board_from_codes(codes + 64 * b);
+  const double LAMBDA_MIN = 0.0001, LAMBDA_MAX = 10.0;
+  auto t0 = std::chrono::steady_clock::now();
+  for (long c = 0; c < n_cases; ++c) {
+    network::Optimizer::optimize(n, boards[c], targets[c], *lambda);
+    if (*lambda < LAMBDA_MIN || LAMBDA_MAX < *lambda) {
+      *lambda = network::Optimizer::DEFAULT_INITIAL_LAMBDA;
+      network::Optimizer::dropout(n);
+    }
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  for (auto *b : boards) delete b;
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+void ref_dropout(void *net, double rate) { network::Optimizer::dropout(static_cast<network::Network *>(net), rate); }
+
+// math::random(): the default-seeded generator owned by math_util.cpp (math_util.h:35-36 makes it per-TU static,
+// so init::initializeRNG never reaches it)
+double ref_math_random() { return math::random(); }
+
+// ---- Decider::prediction on a position given as a board text file ---------------------------------------
+// Returns eval, number of moves and (up to cap) logits in std::map<Move,double> iteration order.
+int ref_prediction_file(void *net, const char *board_path, int white_to_move, double *eval_out, double *logits_out,
+                        int cap) {
+  auto *n = static_cast<network::Network *>(net);
+  auto *g = new game::Game(8, 8);
+  g->board()->loadFromFile(board_path);
+  if (!white_to_move) g->_current_player_color = piece::PieceColor::BLACK;
+  g->generatePossibleMoveVectors();  // refresh cached move lists for the loaded position (game.cpp:892-897)
+  auto pr = n->prediction(g);
+  *eval_out = pr.first;
+  int k = 0;
+  for (auto &kv : pr.second) {
+    if (k < cap) logits_out[k] = kv.second;
+    ++k;
+  }
+  delete g;
+  return k;
+}
+
+}  // extern "C"
