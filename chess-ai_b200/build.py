@@ -1,0 +1,54 @@
+"""Builds libchessai_b200.so (CUDA kernels + C ABI) in-tree with nvcc for sm_100a.
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot. nvcc cross-compiles without a GPU.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libchessai_b200.so")
+SOURCES = ["cab_api.cu", "cab_train.cu"]
+HEADERS = ["cab_internal.cuh", "mlp_stream_kernel.cuh", os.path.join("..", "..", "include", "chessai_b200.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2",
+    "--expt-relaxed-constexpr",
+]
+# private static C++ runtime: the library must not interpose libstdc++ symbols of the host process (python/torch)
+LINK = ["-shared", "-cudart", "shared", "-Xlinker", "--exclude-libs=ALL", "-Xlinker", "-Bsymbolic",
+        "-Xcompiler", "-static-libstdc++,-static-libgcc", "-ldl"]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(verbose=False, force=False):
+    os.makedirs(LIB_DIR, exist_ok=True)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    objs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(LIB_DIR, s.replace(".cu", ".o"))
+        if force or _stale(obj, deps):
+            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            subprocess.check_call(cmd)
+        objs.append(obj)
+    if force or _stale(LIB, objs):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a"] + LINK + objs + ["-o", LIB])
+    tool = os.path.join(LIB_DIR, "pipe_peaks")
+    tsrc = os.path.join(CSRC, "tools", "pipe_peaks.cu")
+    if force or _stale(tool, [tsrc]):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-w", tsrc, "-o", tool])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

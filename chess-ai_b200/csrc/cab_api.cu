@@ -1,0 +1,705 @@
+// cab_api.cu — implementation of include/chessai_b200.h: handle management, weight packing, encoder, forward
+// entry points, network_dump text IO. Training lives in cab_train.cu. No CPU fallback anywhere: every compute
+// entry point needs a CUDA device and says so when there is none.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "cab_internal.cuh"
+#include "mlp_stream_kernel.cuh"
+
+namespace cab {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  set_error("CUDA error '%s' in %s at %s:%d", cudaGetErrorString(e), what, file, line);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return CAB_ENODEVICE;
+  return CAB_ECUDA;
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------------------
+
+// K0 board encoder: piece records -> int8 codes. Integer-only, bit-exact with Piece::code()/0.4
+// (/root/reference/src/chess/piece.cpp:103-105,145-147,179-181,260-262; type/colour tables piece.fwd.h:122-133,287-308).
+// HBM-bound byte kernel: 192 B in, 64 B out per board; each thread encodes 4 squares (12 B in as 3 words, 4 B out).
+__global__ void __launch_bounds__(256) encode_kernel(const uint32_t *__restrict__ rec_words, long n_quads,
+                                                      uint32_t *__restrict__ codes_words) {
+  // base code by type: none 0, king 1, queen 3, rook 4, knight 6, bishop 7, pawn 8; flag adds 1 for king/rook/pawn
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n_quads; i += (long) gridDim.x * blockDim.x) {
+    const uint32_t w0 = rec_words[3 * i], w1 = rec_words[3 * i + 1], w2 = rec_words[3 * i + 2];
+    const uint64_t lo = ((uint64_t) w1 << 32) | w0;
+    uint32_t outw = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      // bytes 3s, 3s+1, 3s+2 of the 12-byte group
+      const int b0 = 3 * s;
+      auto byte_at = [&](int b) -> uint32_t { return b < 8 ? (uint32_t) (lo >> (8 * b)) & 0xffu : (w2 >> (8 * (b - 8))) & 0xffu; };
+      const uint32_t type = byte_at(b0), color = byte_at(b0 + 1), flag = byte_at(b0 + 2);
+      int k = 0;
+      if (type >= 1 && type <= 6 && (color == 1 || color == 2)) {
+        k = (int) ((0x876431u >> (4 * (type - 1))) & 0xfu);  // nibbles: king 1, queen 3, rook 4, knight 6, bishop 7, pawn 8
+        if (flag != 0 && (type == 1 || type == 3 || type == 6)) k += 1;
+        if (color == 2) k = -k;
+      }
+      outw |= ((uint32_t) (uint8_t) (int8_t) k) << (8 * s);
+    }
+    codes_words[i] = outw;
+  }
+}
+
+// weights -> DMMA B-fragment stream (see cab_internal.cuh). One thread per packed double.
+__global__ void __launch_bounds__(256) prepack_kernel(const double *__restrict__ w, double *__restrict__ pack,
+                                                       const PackSeg *__restrict__ segs, int n_segs, long total) {
+  for (long idx = blockIdx.x * (long) blockDim.x + threadIdx.x; idx < total; idx += (long) gridDim.x * blockDim.x) {
+    int si = 0;
+    while (si + 1 < n_segs && idx >= segs[si + 1].dst_off) ++si;
+    const PackSeg sg = segs[si];
+    const long local = idx - sg.dst_off;
+    const int h = (int) (local & 1), lane = (int) ((local >> 1) & 31);
+    const long rest = local >> 6;
+    const int j = (int) (rest % sg.nb), t = (int) (rest / sg.nb);
+    const int kin = 8 * t + 2 * (lane & 3) + h;          // contraction index (feature of the layer input side)
+    const int nout = 8 * (sg.tile0 + j) + (lane >> 2);   // output feature
+    double v = 0.0;
+    if (!sg.transposed) {
+      if (kin < sg.K && nout < sg.N) v = w[sg.w_off + (long) kin * sg.N + nout];
+    } else {  // stream of W^T: contraction over N (kin indexes N), outputs over K (nout indexes K)
+      if (kin < sg.N && nout < sg.K) v = w[sg.w_off + (long) nout * sg.N + kin];
+    }
+    pack[idx] = v;
+  }
+}
+
+// Network::randomNetwork (network.cpp:167-173): U(-1,1) per weight; Philox counter = (w, stream), words 2,3 -> uniform
+__global__ void __launch_bounds__(256) randomize_kernel(double *__restrict__ w, long n, uint64_t seed, uint64_t stream) {
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t) i, (uint32_t) ((uint64_t) i >> 32), (uint32_t) stream, (uint32_t) (stream >> 32),
+                  (uint32_t) seed, (uint32_t) (seed >> 32), r);
+    w[i] = 2.0 * u53(r[2], r[3]) + -1.0;
+  }
+}
+
+// ---- pipe-peak probes (roofline denominators that MEASURED_PEAKS.json lacks) -------------------------------------
+__global__ void __launch_bounds__(256) peak_dmma_kernel(double *out, int iters, double seed) {
+  double c[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { c[i][0] = seed + i; c[i][1] = seed - i; }
+  const double a = seed * 1e-3 + threadIdx.x * 1e-9, b = seed * 1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmma884(c[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) peak_dfma_kernel(double *out, int iters, double seed) {
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = seed + i + threadIdx.x;
+  const double a = seed * 1.0000001, b = seed * 0.5;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) peak_ffma_kernel(float *out, int iters, float seed) {
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = seed + i + threadIdx.x;
+  const float a = seed * 1.0000001f, b = seed * 0.5f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], a, b);
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += acc[i];
+  if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---- host: stream plans ------------------------------------------------------------------------------------------
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Forward stream: layer l contracts over dims[l] (input units) and produces dims[l+1] (output tiles).
+// Backward stream (transposed): weight layer l contracts over dims[l+1] and produces dims[l]; layers go top-down
+// and layer 0 is skipped (omega of the input layer is never used, network.cpp:257 / SURVEY Q10).
+static void build_plan(const cab_net *net, bool transposed, StreamPlan *plan) {
+  plan->chunks.clear();
+  plan->segs.clear();
+  const int L = (int) net->dims.size();
+  long off = 0;  // doubles
+  bool single_block = true;
+  int max_units = 8;
+  std::vector<int> order;
+  if (!transposed) for (int l = 0; l + 1 < L; ++l) order.push_back(l);
+  else for (int l = L - 2; l >= 1; --l) order.push_back(l);
+  for (int l : order) {
+    const int in_w = transposed ? net->dims[l + 1] : net->dims[l], out_w = transposed ? net->dims[l] : net->dims[l + 1];
+    if (ceil_div(out_w, 8) > kMaxNB) single_block = false;
+    max_units = std::max(max_units, std::max(ceil_div(in_w, 8), ceil_div(out_w, 8)));
+  }
+  // activation buffer: in place when every layer fits one n-block, ping-pong otherwise
+  plan->a_units = single_block ? max_units : 2 * max_units;
+  int ping = 0;
+  for (size_t oi = 0; oi < order.size(); ++oi) {
+    const int l = order[oi];
+    const int K = net->dims[l], N = net->dims[l + 1];
+    const int in_w = transposed ? N : K, out_w = transposed ? K : N;
+    const int t_in = ceil_div(in_w, 8), n_tiles = ceil_div(out_w, 8);
+    const int n_blocks = ceil_div(n_tiles, kMaxNB);
+    const int a_in = single_block ? 0 : ping * max_units, a_out_base = single_block ? 0 : (1 - ping) * max_units;
+    int tile0 = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+      const int nb = (n_tiles - tile0 + (n_blocks - b) - 1) / (n_blocks - b);  // balanced split
+      PackSeg sg{};
+      sg.dst_off = off;
+      sg.w_off = net->woff[l];
+      sg.K = K; sg.N = N;
+      sg.t_in = t_in; sg.tile0 = tile0; sg.nb = nb; sg.transposed = transposed ? 1 : 0;
+      sg.n_doubles = (long) t_in * nb * 64;
+      plan->segs.push_back(sg);
+      const int per_t_bytes = nb * kUnitBytes;
+      const int tpc = std::max(1, kStageBytes / per_t_bytes);
+      for (int t0 = 0; t0 < t_in; t0 += tpc) {
+        ChunkDesc d{};
+        d.tcount = (uint16_t) std::min(tpc, t_in - t0);
+        d.t0 = (uint16_t) t0;
+        d.src_off = (uint32_t) ((off + (long) t0 * nb * 64) * 8);
+        d.bytes = (uint32_t) (d.tcount * per_t_bytes);
+        d.tile0 = (uint16_t) tile0;
+        d.nb = (uint8_t) nb;
+        d.flags = 0;
+        if (t0 == 0) d.flags |= kFirst;
+        if (t0 + tpc >= t_in) d.flags |= kLast;
+        if (oi + 1 == order.size() && b + 1 == n_blocks && (d.flags & kLast)) d.flags |= kFinal;
+        d.a_in = (uint16_t) a_in;
+        d.a_out = (uint16_t) (a_out_base + tile0);
+        d.layer = (uint16_t) l;
+        d.n_tiles = (uint16_t) n_tiles;
+        d.save_off = transposed ? net->act_unit_off[l] : net->act_unit_off[l + 1];
+        d.n_real = (uint32_t) out_w;
+        plan->chunks.push_back(d);
+      }
+      off += sg.n_doubles;
+      tile0 += nb;
+    }
+    ping = 1 - ping;
+  }
+  plan->total_doubles = off;
+}
+
+static int upload_plan(StreamPlan *plan) {
+  if (plan->total_doubles == 0) return CAB_OK;
+  CAB_CUDA(cudaMalloc(&plan->d_chunks, plan->chunks.size() * sizeof(ChunkDesc)));
+  CAB_CUDA(cudaMemcpy(plan->d_chunks, plan->chunks.data(), plan->chunks.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice));
+  CAB_CUDA(cudaMalloc(&plan->d_segs, plan->segs.size() * sizeof(PackSeg)));
+  CAB_CUDA(cudaMemcpy(plan->d_segs, plan->segs.data(), plan->segs.size() * sizeof(PackSeg), cudaMemcpyHostToDevice));
+  CAB_CUDA(cudaMalloc(&plan->d_pack, plan->total_doubles * sizeof(double)));
+  return CAB_OK;
+}
+
+static void free_plan(StreamPlan *plan) {
+  cudaFree(plan->d_chunks); cudaFree(plan->d_segs); cudaFree(plan->d_pack);
+  plan->d_chunks = nullptr; plan->d_segs = nullptr; plan->d_pack = nullptr;
+}
+
+size_t forward_smem_bytes(int a_units) {
+  return (size_t) kStages * kStageBytes + (size_t) kConsumerWarps * a_units * kUnitBytes + 2 * kStages * sizeof(uint64_t);
+}
+
+// (re)build the packed streams from d_w on `stream`
+int ensure_packed(cab_net *net, cudaStream_t stream) {
+  if (!net->pack_dirty) return CAB_OK;
+  for (StreamPlan *p : {&net->fwd, &net->bwd}) {
+    if (p->total_doubles == 0) continue;
+    const int grid = (int) std::min<long>((p->total_doubles + 255) / 256, 148L * 16);
+    prepack_kernel<<<grid, 256, 0, stream>>>(net->d_w, p->d_pack, p->d_segs, (int) p->segs.size(), p->total_doubles);
+    net->launches++;
+  }
+  CAB_CUDA(cudaGetLastError());
+  net->pack_dirty = false;
+  return CAB_OK;
+}
+
+int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d_out, double *d_save, long save_stride,
+                   cudaStream_t stream) {
+  if (n_boards <= 0) return CAB_OK;
+  ForwardArgs a{};
+  a.pack = reinterpret_cast<const uint8_t *>(net->fwd.d_pack);
+  a.chunks = net->fwd.d_chunks;
+  a.n_chunks = (int) net->fwd.chunks.size();
+  a.a_units = net->fwd.a_units;
+  a.n_boards = n_boards;
+  a.n_groups = (n_boards + kBoardsPerCta - 1) / kBoardsPerCta;
+  a.codes = d_codes;
+  a.out = d_out;
+  a.save = d_save;
+  a.save_stride = save_stride;
+  const size_t smem = forward_smem_bytes(a.a_units);
+  const int per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
+  const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * per_sm);
+  mlp_forward_kernel<<<grid, kThreads, smem, stream>>>(a);
+  net->launches++;
+  CAB_CUDA(cudaGetLastError());
+  return CAB_OK;
+}
+
+static int select_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s): libchessai_b200 has no CPU fallback", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+    return CAB_ENODEVICE;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device %d out of range (have %d)", device, n);
+    return CAB_EINVAL;
+  }
+  CAB_CUDA(cudaSetDevice(device));
+  return CAB_OK;
+}
+
+static std::vector<int> normalize_dims(const int *dims, int n) {  // network.cpp:39-56
+  std::vector<int> d;
+  const std::vector<int> def = {64, 144, 225, 100, 1};
+  if (dims == nullptr || n <= 0) return def;
+  d.assign(dims, dims + n);
+  if (d[0] != 64) d.insert(d.begin(), 64);
+  if (d.back() != 1) d.push_back(1);
+  if (d.size() <= 2) return def;
+  return d;
+}
+
+static int create_exact(const std::vector<int> &dims, int device, cab_net **out) {
+  for (int v : dims)
+    if (v <= 0 || v > 8192) { set_error("layer width %d out of range [1, 8192]", v); return CAB_EINVAL; }
+  if (dims.size() < 2 || dims.size() > 32) { set_error("bad layer count %zu", dims.size()); return CAB_EINVAL; }
+  if (dims[0] != 64) { set_error("input layer must be 64 wide (one feature per square), got %d", dims[0]); return CAB_EINVAL; }
+  int rc = select_device(device);
+  if (rc != CAB_OK) return rc;
+  cab_net *net = new cab_net();
+  net->device = device;
+  cudaDeviceProp prop;
+  CAB_CUDA(cudaGetDeviceProperties(&prop, device));
+  net->sm_count = prop.multiProcessorCount;
+  net->dims = dims;
+  long w = 0;
+  uint32_t u = 0;
+  for (size_t l = 0; l < dims.size(); ++l) {
+    net->act_unit_off.push_back(u);
+    u += (uint32_t) ceil_div(dims[l], 8);
+    if (l + 1 < dims.size()) { net->woff.push_back(w); w += (long) dims[l] * dims[l + 1]; }
+  }
+  net->act_units_total = u;
+  net->n_weights = w;
+  CAB_CUDA(cudaMalloc(&net->d_w, w * sizeof(double)));
+  CAB_CUDA(cudaMemset(net->d_w, 0, w * sizeof(double)));
+  build_plan(net, false, &net->fwd);
+  build_plan(net, true, &net->bwd);
+  if ((rc = upload_plan(&net->fwd)) != CAB_OK) return rc;
+  if ((rc = upload_plan(&net->bwd)) != CAB_OK) return rc;
+  const size_t smem = forward_smem_bytes(std::max(net->fwd.a_units, net->bwd.a_units));
+  if (smem > 227 * 1024) {
+    set_error("layer too wide for the fp64 stream kernel: needs %zu B shared memory", smem);
+    delete net;
+    return CAB_EINVAL;
+  }
+  CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  net->pack_dirty = true;
+  *out = net;
+  return CAB_OK;
+}
+
+EvalCtx *acquire_ctx(cab_net *net) {
+  std::lock_guard<std::mutex> lk(net->mu);
+  for (EvalCtx *c : net->ctxs)
+    if (!c->busy) { c->busy = true; return c; }
+  EvalCtx *c = new EvalCtx();
+  c->busy = true;
+  net->ctxs.push_back(c);
+  return c;
+}
+void release_ctx(cab_net *net, EvalCtx *c) {
+  std::lock_guard<std::mutex> lk(net->mu);
+  c->busy = false;
+}
+
+constexpr long kEvalChunkBoards = 131072;  // host<->device pipelining granularity of the *_host entry points
+
+static int ctx_reserve(EvalCtx *c, long boards, bool records) {
+  for (int i = 0; i < 2; ++i)
+    if (c->stream[i] == nullptr) CAB_CUDA(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
+  if (boards > c->cap_boards) {
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(c->d_codes[i]); cudaFree(c->d_out[i]); cudaFree(c->d_records[i]);
+      c->d_records[i] = nullptr;
+      CAB_CUDA(cudaMalloc(&c->d_codes[i], boards * 64));
+      CAB_CUDA(cudaMalloc(&c->d_out[i], boards * sizeof(double)));
+    }
+    c->cap_boards = boards;
+  }
+  if (records)
+    for (int i = 0; i < 2; ++i)
+      if (c->d_records[i] == nullptr) CAB_CUDA(cudaMalloc(&c->d_records[i], c->cap_boards * 192));
+  return CAB_OK;
+}
+
+static int eval_host_impl(cab_net *net, const int8_t *codes, const uint8_t *records, long n, double *out) {
+  int rc = select_device(net->device);
+  if (rc != CAB_OK) return rc;
+  EvalCtx *c = acquire_ctx(net);
+  const long chunk = std::min(n, kEvalChunkBoards);
+  rc = ctx_reserve(c, chunk, records != nullptr);
+  if (rc == CAB_OK) {
+    {
+      std::lock_guard<std::mutex> lk(net->mu);
+      rc = ensure_packed(net, c->stream[0]);
+      if (rc == CAB_OK && cudaStreamSynchronize(c->stream[0]) != cudaSuccess) rc = CAB_ECUDA;
+    }
+    int i = 0;
+    for (long b0 = 0; b0 < n && rc == CAB_OK; b0 += chunk, i ^= 1) {
+      const long nb = std::min(chunk, n - b0);
+      cudaStream_t s = c->stream[i];
+      if (records != nullptr) {
+        if (cudaMemcpyAsync(c->d_records[i], records + b0 * 192, nb * 192, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = CAB_ECUDA; break; }
+        rc = cab_encode_dev(c->d_records[i], nb, c->d_codes[i], s);
+        net->launches++;
+      } else {
+        if (cudaMemcpyAsync(c->d_codes[i], codes + b0 * 64, nb * 64, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = CAB_ECUDA; break; }
+      }
+      if (rc == CAB_OK) rc = launch_forward(net, c->d_codes[i], nb, c->d_out[i], nullptr, 0, s);
+      if (rc == CAB_OK && cudaMemcpyAsync(out + b0, c->d_out[i], nb * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = CAB_ECUDA;
+    }
+    for (int k = 0; k < 2; ++k)
+      if (cudaStreamSynchronize(c->stream[k]) != cudaSuccess && rc == CAB_OK) rc = CAB_ECUDA;
+    if (rc == CAB_ECUDA) set_error("CUDA failure in eval: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  release_ctx(net, c);
+  return rc;
+}
+
+}  // namespace cab
+
+using namespace cab;
+
+// ================================================================================================================
+extern "C" {
+
+int cab_version(void) { return 1; }
+const char *cab_last_error(void) { return g_err; }
+
+int cab_device_count(int *count) {
+  if (!count) { set_error("null argument"); return CAB_EINVAL; }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count = 0; return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__); }
+  *count = n;
+  return CAB_OK;
+}
+
+int cab_net_create(const int *dims, int n_dims, int device, cab_net **out) {
+  if (!out) { set_error("null argument"); return CAB_EINVAL; }
+  *out = nullptr;
+  return create_exact(normalize_dims(dims, n_dims), device, out);
+}
+
+int cab_net_destroy(cab_net *net) {
+  if (!net) return CAB_OK;
+  cudaSetDevice(net->device);
+  cab_dp_shutdown(net);
+  for (EvalCtx *c : net->ctxs) {
+    for (int i = 0; i < 2; ++i) {
+      if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
+      cudaFree(c->d_codes[i]); cudaFree(c->d_out[i]); cudaFree(c->d_records[i]);
+    }
+    delete c;
+  }
+  free_plan(&net->fwd); free_plan(&net->bwd);
+  cudaFree(net->d_w); cudaFree(net->d_dw); cudaFree(net->d_grad); cudaFree(net->d_acts); cudaFree(net->d_psis);
+  cudaFree(net->d_tcodes); cudaFree(net->d_ttargets); cudaFree(net->d_tout); cudaFree(net->d_scalars);
+  if (net->train_stream) cudaStreamDestroy(net->train_stream);
+  delete net;
+  return CAB_OK;
+}
+
+int cab_net_clone(const cab_net *net, cab_net **out) {  // Network::clone — weights only (network.cpp:195-205)
+  if (!net || !out) { set_error("null argument"); return CAB_EINVAL; }
+  int rc = create_exact(net->dims, net->device, out);
+  if (rc != CAB_OK) return rc;
+  CAB_CUDA(cudaMemcpy((*out)->d_w, net->d_w, net->n_weights * sizeof(double), cudaMemcpyDeviceToDevice));
+  (*out)->pack_dirty = true;
+  return CAB_OK;
+}
+
+int cab_net_num_layers(const cab_net *net, int *n) {
+  if (!net || !n) { set_error("null argument"); return CAB_EINVAL; }
+  *n = (int) net->dims.size();
+  return CAB_OK;
+}
+int cab_net_dims(const cab_net *net, int *dims_out) {
+  if (!net || !dims_out) { set_error("null argument"); return CAB_EINVAL; }
+  for (size_t i = 0; i < net->dims.size(); ++i) dims_out[i] = net->dims[i];
+  return CAB_OK;
+}
+int cab_net_num_weights(const cab_net *net, long *n) {
+  if (!net || !n) { set_error("null argument"); return CAB_EINVAL; }
+  *n = net->n_weights;
+  return CAB_OK;
+}
+int cab_net_device(const cab_net *net, int *device) {
+  if (!net || !device) { set_error("null argument"); return CAB_EINVAL; }
+  *device = net->device;
+  return CAB_OK;
+}
+
+int cab_net_set_weights(cab_net *net, const double *w, long n) {
+  if (!net || !w) { set_error("null argument"); return CAB_EINVAL; }
+  if (n != net->n_weights) { set_error("expected %ld weights, got %ld", net->n_weights, n); return CAB_EINVAL; }
+  int rc = select_device(net->device);
+  if (rc != CAB_OK) return rc;
+  CAB_CUDA(cudaDeviceSynchronize());
+  CAB_CUDA(cudaMemcpy(net->d_w, w, n * sizeof(double), cudaMemcpyHostToDevice));
+  net->pack_dirty = true;
+  return CAB_OK;
+}
+
+int cab_net_get_weights(const cab_net *net, double *w, long n) {
+  if (!net || !w) { set_error("null argument"); return CAB_EINVAL; }
+  if (n != net->n_weights) { set_error("expected %ld weights, got %ld", net->n_weights, n); return CAB_EINVAL; }
+  int rc = select_device(net->device);
+  if (rc != CAB_OK) return rc;
+  CAB_CUDA(cudaDeviceSynchronize());
+  CAB_CUDA(cudaMemcpy(w, net->d_w, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return CAB_OK;
+}
+
+int cab_net_randomize(cab_net *net, uint64_t seed, uint64_t stream) {
+  if (!net) { set_error("null argument"); return CAB_EINVAL; }
+  int rc = select_device(net->device);
+  if (rc != CAB_OK) return rc;
+  randomize_kernel<<<(int) std::min<long>((net->n_weights + 255) / 256, 148L * 8), 256>>>(net->d_w, net->n_weights, seed, stream);
+  net->launches++;
+  CAB_CUDA(cudaGetLastError());
+  CAB_CUDA(cudaDeviceSynchronize());
+  net->pack_dirty = true;
+  return CAB_OK;
+}
+
+int cab_net_zero(cab_net *net) {
+  if (!net) { set_error("null argument"); return CAB_EINVAL; }
+  int rc = select_device(net->device);
+  if (rc != CAB_OK) return rc;
+  CAB_CUDA(cudaDeviceSynchronize());
+  CAB_CUDA(cudaMemset(net->d_w, 0, net->n_weights * sizeof(double)));
+  net->pack_dirty = true;
+  return CAB_OK;
+}
+
+// ---- network_dump text ------------------------------------------------------------------------------------------
+int cab_net_load_text(const char *path, int device, cab_net **out) {
+  if (!path || !out) { set_error("null argument"); return CAB_EINVAL; }
+  *out = nullptr;
+  FILE *f = fopen(path, "rb");
+  if (!f) { set_error("cannot open network dump '%s'", path); return CAB_EIO; }
+  int L = 0;
+  if (fscanf(f, "%d", &L) != 1 || L < 2 || L > 32) { fclose(f); set_error("'%s': bad layer count", path); return CAB_EIO; }
+  std::vector<int> dims(L);
+  for (int l = 0; l < L; ++l)
+    if (fscanf(f, "%d", &dims[l]) != 1) { fclose(f); set_error("'%s': bad dimension list", path); return CAB_EIO; }
+  long nw = 0;
+  for (int l = 0; l + 1 < L; ++l) nw += (long) dims[l] * dims[l + 1];
+  if (nw <= 0 || nw > (1L << 31)) { fclose(f); set_error("'%s': implausible weight count %ld", path, nw); return CAB_EIO; }
+  std::vector<double> w(nw);
+  // whitespace-delimited tokens, like operator>> (network.cpp:401-404); strtod on a slurped buffer is ~10x faster than fscanf
+  long pos = ftell(f);
+  fseek(f, 0, SEEK_END);
+  long end = ftell(f);
+  fseek(f, pos, SEEK_SET);
+  std::vector<char> buf(end - pos + 1);
+  size_t got = fread(buf.data(), 1, end - pos, f);
+  fclose(f);
+  buf[got] = 0;
+  char *p = buf.data();
+  for (long i = 0; i < nw; ++i) {
+    char *q = nullptr;
+    w[i] = strtod(p, &q);
+    if (q == p) { set_error("'%s': expected %ld weights, found %ld", path, nw, i); return CAB_EIO; }
+    p = q;
+  }
+  int rc = create_exact(dims, device, out);
+  if (rc != CAB_OK) return rc;
+  rc = cab_net_set_weights(*out, w.data(), nw);
+  if (rc != CAB_OK) { cab_net_destroy(*out); *out = nullptr; }
+  return rc;
+}
+
+int cab_net_dump_text(const cab_net *net, const char *path) {
+  if (!net || !path) { set_error("null argument"); return CAB_EINVAL; }
+  std::vector<double> w(net->n_weights);
+  int rc = cab_net_get_weights(net, w.data(), net->n_weights);
+  if (rc != CAB_OK) return rc;
+  FILE *f = fopen(path, "wb");
+  if (!f) { set_error("cannot open '%s' for writing", path); return CAB_EIO; }
+  const int L = (int) net->dims.size();
+  fprintf(f, "%d\n", L);                                      // network.cpp:411
+  for (int l = 0; l + 1 < L; ++l) fprintf(f, "%d ", net->dims[l]);
+  fprintf(f, "%d\n", net->dims[L - 1]);                       // network.cpp:414-416
+  for (long i = 0; i < net->n_weights; ++i) fprintf(f, "%.17e ", w[i]);  // string::from_double + " " (network.cpp:422)
+  if (fclose(f) != 0) { set_error("write to '%s' failed", path); return CAB_EIO; }
+  return CAB_OK;
+}
+
+// ---- encoder ----------------------------------------------------------------------------------------------------
+int cab_encode_dev(const uint8_t *records_dev, long n_boards, int8_t *codes_dev, void *stream) {
+  if (n_boards < 0 || (n_boards > 0 && (!records_dev || !codes_dev))) { set_error("bad argument"); return CAB_EINVAL; }
+  if (n_boards == 0) return CAB_OK;
+  const long quads = n_boards * 16;
+  const int grid = (int) std::min<long>((quads + 255) / 256, 148L * 16);
+  encode_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(reinterpret_cast<const uint32_t *>(records_dev), quads,
+                                                         reinterpret_cast<uint32_t *>(codes_dev));
+  CAB_CUDA(cudaGetLastError());
+  return CAB_OK;
+}
+
+int cab_encode_host(int device, const uint8_t *records, long n, int8_t *codes) {
+  if (n < 0 || (n > 0 && (!records || !codes))) { set_error("bad argument"); return CAB_EINVAL; }
+  int rc = select_device(device);
+  if (rc != CAB_OK || n == 0) return rc;
+  uint8_t *d_r = nullptr;
+  int8_t *d_c = nullptr;
+  CAB_CUDA(cudaMalloc(&d_r, n * 192));
+  CAB_CUDA(cudaMalloc(&d_c, n * 64));
+  CAB_CUDA(cudaMemcpy(d_r, records, n * 192, cudaMemcpyHostToDevice));
+  rc = cab_encode_dev(d_r, n, d_c, nullptr);
+  if (rc == CAB_OK && cudaMemcpy(codes, d_c, n * 64, cudaMemcpyDeviceToHost) != cudaSuccess) rc = CAB_ECUDA;
+  cudaFree(d_r); cudaFree(d_c);
+  return rc;
+}
+
+// ---- forward ----------------------------------------------------------------------------------------------------
+int cab_eval_dev(cab_net *net, const int8_t *codes_dev, long n, double *out_dev, void *stream) {
+  if (!net || n < 0 || (n > 0 && (!codes_dev || !out_dev))) { set_error("bad argument"); return CAB_EINVAL; }
+  int rc = select_device(net->device);
+  if (rc != CAB_OK) return rc;
+  {
+    std::lock_guard<std::mutex> lk(net->mu);
+    if (net->pack_dirty) {
+      rc = ensure_packed(net, (cudaStream_t) stream);
+      if (rc != CAB_OK) return rc;
+      CAB_CUDA(cudaStreamSynchronize((cudaStream_t) stream));  // other streams may evaluate next
+    }
+  }
+  return launch_forward(net, codes_dev, n, out_dev, nullptr, 0, (cudaStream_t) stream);
+}
+
+int cab_eval_host(cab_net *net, const int8_t *codes, long n, double *out) {
+  if (!net || n < 0 || (n > 0 && (!codes || !out))) { set_error("bad argument"); return CAB_EINVAL; }
+  if (n == 0) return CAB_OK;
+  return eval_host_impl(net, codes, nullptr, n, out);
+}
+
+int cab_eval_records_host(cab_net *net, const uint8_t *records, long n, double *out) {
+  if (!net || n < 0 || (n > 0 && (!records || !out))) { set_error("bad argument"); return CAB_EINVAL; }
+  if (n == 0) return CAB_OK;
+  return eval_host_impl(net, nullptr, records, n, out);
+}
+
+int cab_forward_full_host(cab_net *net, const int8_t *codes, long n, double *acts_host) {
+  if (!net || n < 0 || (n > 0 && (!codes || !acts_host))) { set_error("bad argument"); return CAB_EINVAL; }
+  if (n == 0) return CAB_OK;
+  int rc = select_device(net->device);
+  if (rc != CAB_OK) return rc;
+  const long pad = (n + kBoardsPerCta - 1) / kBoardsPerCta * kBoardsPerCta;
+  const long stride = pad * 8;
+  int8_t *d_codes = nullptr;
+  double *d_save = nullptr, *d_out = nullptr;
+  CAB_CUDA(cudaMalloc(&d_codes, n * 64));
+  CAB_CUDA(cudaMalloc(&d_out, n * sizeof(double)));
+  CAB_CUDA(cudaMalloc(&d_save, (size_t) net->act_units_total * stride * sizeof(double)));
+  CAB_CUDA(cudaMemset(d_save, 0, (size_t) net->act_units_total * stride * sizeof(double)));
+  CAB_CUDA(cudaMemcpy(d_codes, codes, n * 64, cudaMemcpyHostToDevice));
+  {
+    std::lock_guard<std::mutex> lk(net->mu);
+    rc = ensure_packed(net, nullptr);
+  }
+  if (rc == CAB_OK) rc = launch_forward(net, d_codes, n, d_out, d_save, stride, nullptr);
+  std::vector<double> h((size_t) net->act_units_total * stride);
+  if (rc == CAB_OK && cudaMemcpy(h.data(), d_save, h.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = CAB_ECUDA;
+  cudaFree(d_codes); cudaFree(d_out); cudaFree(d_save);
+  if (rc != CAB_OK) return rc;
+  // unit layout [unit][board][8] -> board-major rows of sum(dims[1..]) doubles
+  long row = 0;
+  for (size_t l = 1; l < net->dims.size(); ++l) row += net->dims[l];
+  for (long b = 0; b < n; ++b) {
+    long o = 0;
+    for (size_t l = 1; l < net->dims.size(); ++l)
+      for (int j = 0; j < net->dims[l]; ++j, ++o)
+        acts_host[b * row + o] = h[(size_t) (net->act_unit_off[l] + j / 8) * stride + b * 8 + (j % 8)];
+  }
+  return CAB_OK;
+}
+
+// ---- measurement helpers ----------------------------------------------------------------------------------------
+int cab_measure_pipe_peak(int device, int kind, double *tflops) {
+  if (!tflops || kind < 0 || kind > 2) { set_error("bad argument"); return CAB_EINVAL; }
+  int rc = select_device(device);
+  if (rc != CAB_OK) return rc;
+  cudaDeviceProp prop;
+  CAB_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int grid = prop.multiProcessorCount * 2, iters = 4096;
+  double *d = nullptr;
+  CAB_CUDA(cudaMalloc(&d, (size_t) grid * 256 * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CAB_CUDA(cudaEventCreate(&e0));
+  CAB_CUDA(cudaEventCreate(&e1));
+  auto launch = [&] {
+    if (kind == 0) peak_dmma_kernel<<<grid, 256>>>(d, iters, 1.0);
+    else if (kind == 1) peak_dfma_kernel<<<grid, 256>>>(d, iters, 1.0);
+    else peak_ffma_kernel<<<grid, 256>>>((float *) d, iters, 1.0f);
+  };
+  for (int i = 0; i < 3; ++i) launch();
+  CAB_CUDA(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < 10; ++r) {
+    cudaEventRecord(e0);
+    launch();
+    cudaEventRecord(e1);
+    CAB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = ms < best ? ms : best;
+  }
+  double flop;
+  if (kind == 0) flop = 2.0 * 256 * 16 * iters * (double) grid * 8;
+  else if (kind == 1) flop = 2.0 * 16 * iters * (double) grid * 256;
+  else flop = 2.0 * 32 * iters * (double) grid * 256;
+  *tflops = flop / best * 1e-9;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  CAB_CUDA(cudaGetLastError());
+  return CAB_OK;
+}
+
+int cab_net_launch_count(const cab_net *net, long *launches) {
+  if (!net || !launches) { set_error("null argument"); return CAB_EINVAL; }
+  *launches = net->launches.load();
+  return CAB_OK;
+}
+
+}  // extern "C"

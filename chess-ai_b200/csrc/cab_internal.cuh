@@ -1,0 +1,195 @@
+// cab_internal.cuh — shared declarations for the CUDA side of libchessai_b200.so (not part of the ABI).
+//
+// Data layout in HBM:
+//   w            flat fp64 weights, n,i,j order (the dump's line 3)                     n_weights * 8 B
+//   pack_fwd     the same weights re-ordered into the DMMA B-fragment stream consumed by the forward kernel
+//   pack_bwd     W^T in the same fragment order, consumed by the backward (omega) kernel
+//   chunk tables descriptors of the <=16 KB pieces of those streams that one bulk copy moves to shared memory
+// "unit"  = 8 consecutive features of 8 boards held as 32 lanes x double2 (512 B): lane (m = lane>>2, q = lane&3)
+//           holds features 8t+2q, 8t+2q+1 of board m. It is simultaneously the DMMA C-fragment of an output tile
+//           and the A-fragment pair of the next layer's two k-steps, so activations never change layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/chessai_b200.h"
+
+namespace cab {
+
+constexpr int kConsumerWarps = 4;                       // warps doing DMMA; each owns 8 boards
+constexpr int kThreads = (kConsumerWarps + 1) * 32;     // + 1 producer warp issuing bulk copies
+constexpr int kBoardsPerWarp = 8;
+constexpr int kBoardsPerCta = kConsumerWarps * kBoardsPerWarp;
+constexpr int kStages = 3;                              // weight ring depth
+constexpr int kStageBytes = 16384;                      // one ring slot
+constexpr int kMaxNB = 32;                              // output tiles accumulated in registers at once
+constexpr int kUnitBytes = 512;                         // 32 lanes x double2
+
+enum ChunkFlags : uint8_t { kFirst = 1, kLast = 2, kFinal = 4 };
+
+struct __align__(16) ChunkDesc {
+  uint32_t src_off;  // byte offset into the packed stream
+  uint32_t bytes;    // multiple of 512
+  uint16_t t0;       // first input unit covered by this chunk
+  uint16_t tcount;   // input units in this chunk
+  uint16_t tile0;    // first output tile of the n-block
+  uint8_t nb;        // tiles in the n-block (1..kMaxNB)
+  uint8_t flags;     // ChunkFlags
+  uint16_t a_in;     // unit offset of the layer input inside the per-warp activation buffer
+  uint16_t a_out;    // unit offset of this n-block's output
+  uint16_t layer;    // weight layer index (0-based)
+  uint16_t n_tiles;  // output tiles of the whole layer
+  uint32_t save_off; // unit offset of this layer's output inside the saved-activation tensor (x n_boards_pad)
+  uint32_t n_real;   // real (unpadded) output width of the layer
+};
+static_assert(sizeof(ChunkDesc) == 32, "ChunkDesc must stay 32 bytes");
+
+struct PackSeg {  // one (layer, n-block) piece of a packed stream, for the prepack kernel
+  long dst_off;   // in doubles
+  long w_off;     // offset of the layer's weights in the flat array
+  int K, N;       // layer shape: W is [K][N]
+  int t_in;       // input units
+  int tile0, nb;  // output tiles covered
+  int transposed; // 0: stream of W (forward); 1: stream of W^T (backward: contraction over N, outputs over K)
+  long n_doubles;
+};
+
+struct StreamPlan {  // host description of one packed stream
+  std::vector<ChunkDesc> chunks;
+  std::vector<PackSeg> segs;
+  long total_doubles = 0;
+  int a_units = 0;      // per-warp activation buffer size in units
+  ChunkDesc *d_chunks = nullptr;
+  PackSeg *d_segs = nullptr;
+  double *d_pack = nullptr;
+};
+
+struct EvalCtx {  // per-caller scratch: lets many host threads evaluate on one net concurrently
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  int8_t *d_codes[2] = {nullptr, nullptr};
+  double *d_out[2] = {nullptr, nullptr};
+  uint8_t *d_records[2] = {nullptr, nullptr};
+  long cap_boards = 0;
+  bool busy = false;
+};
+
+}  // namespace cab
+
+struct cab_net {
+  int device = 0;
+  int sm_count = 148;
+  std::vector<int> dims;
+  std::vector<long> woff;
+  long n_weights = 0;
+  double *d_w = nullptr;     // flat weights
+  bool pack_dirty = true;    // packed streams stale w.r.t. d_w
+  cab::StreamPlan fwd, bwd;
+  // saved-activation geometry (units per board-group, per layer)
+  std::vector<uint32_t> act_unit_off;  // per layer l (0..L-1): first unit of layer l's activations
+  uint32_t act_units_total = 0;
+  // training state
+  double *d_dw = nullptr;      // last applied update (connection_changes)
+  double *d_grad = nullptr;    // n_weights + 4 doubles: sum over batch of a*psi, then [sumE, sumE', count, spare]
+  double *d_acts = nullptr;    // saved activations [unit][board_pad][8]
+  double *d_psis = nullptr;    // saved psi, same geometry
+  long train_cap = 0;          // boards the two tensors above can hold
+  int8_t *d_tcodes = nullptr;
+  double *d_ttargets = nullptr;
+  double *d_tout = nullptr;
+  long tbuf_cap = 0;
+  double *d_scalars = nullptr; // small device scratch (lambda, flags ...)
+  cudaStream_t train_stream = nullptr;
+  // data parallel
+  void *nccl_comm = nullptr;
+  int dp_rank = 0, dp_world = 1;
+  // eval contexts
+  std::mutex mu;
+  std::vector<cab::EvalCtx *> ctxs;
+  std::atomic<long> launches{0};
+};
+
+namespace cab {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define CAB_CUDA(call)                                                         \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) return cab::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+// ---- device helpers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar), ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// D(8x8) += A(8x4) * B(4x8) in fp64 on the tensor pipe (SASS: DMMA.8x8x4).
+// lane: A[row = lane>>2][col = lane&3], B[row = lane&3][col = lane>>2], C[row = lane>>2][col = 2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+// The reference activation, as written (mcts_network/network.h:83-94):
+//   f(x) = MAX * modifiedSigmoid(x / WIDTH),  modifiedSigmoid(u) = 2/(1+exp(-2u)) - 1,  MAX = WIDTH = 4
+__device__ __forceinline__ double act_f(double x) { return 4.0 * (2.0 / (1.0 + exp(-2.0 * (x / 4.0))) - 1.0); }
+// f'(x) = MAX * (1 - sig^2) / WIDTH with sig = modifiedSigmoid(x/WIDTH) = f(x)/MAX, so it is a function of a = f(x):
+__device__ __forceinline__ double act_df_from_a(double a) {
+  const double sig = a / 4.0;
+  return 4.0 * (1.0 - sig * sig) / 4.0;
+}
+
+// Philox4x32-10 (Salmon et al. 2011); mirrors oracle/mlp_oracle.c:orc_philox4x32_10 bit for bit
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                       uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t) 0xD2511F53u * c0, p1 = (uint64_t) 0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t) (p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t) p1;
+    const uint32_t n2 = (uint32_t) (p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t) p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__host__ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
+  const uint64_t v = ((uint64_t) hi << 32) | lo;
+  return (double) (v >> 11) * (1.0 / 9007199254740992.0);
+}
+
+}  // namespace cab

@@ -1,0 +1,131 @@
+/* chessai_b200.h — the C ABI of the B200-native MLP evaluator / trainer for utk003/Chess-AI.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types. The reference has no FFI layer —
+ * its boundary is the C++ class API of src/mcts_network/{decider,network}.h — so every entry point below names
+ * the reference member it replaces (file:line under /root/reference/src/). The C++ shim classes in
+ * chess-ai_b200/host/ (network::Network, network::Optimizer, network::NetworkStorage, decider::Decider) keep the
+ * reference signatures and call only this ABI; INTEGRATION.md shows how they slot into src/player and the MCTS loop.
+ *
+ * Conventions
+ *   - every function returns int: 0 = CAB_OK, otherwise a CAB_E* code; the message is in cab_last_error()
+ *     (thread-local). No aborts, no exceptions across the ABI (the reference DEBUG_ASSERTs instead).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns CAB_ENODEVICE.
+ *   - boards travel as 64 int8 "codes" k in [-9, 9], square i = row*8+col (chess/game.h:121-127), row 0 = white
+ *     back rank; the network input is k*0.4 bit-for-bit (chess/piece.cpp:103-105,145-147,179-181,260-262).
+ *     k: 1 K, 2 K(moved), 3 Q, 4 R, 5 R(moved), 6 N, 7 B, 8 P, 9 P(moved2x); black negative; 0 empty.
+ *   - piece records (encoder input) are 3 bytes per square: type {0 none,1 king,2 queen,3 rook,4 knight,5 bishop,
+ *     6 pawn}, colour {0 none,1 white,2 black}, flag {0,1} (King/Rook::_moved, Pawn::_moved2x).
+ *   - weights travel as one flat fp64 array in n,i,j order — exactly line 3 of the network_dump text format
+ *     (mcts_network/network.cpp:418-422).
+ *   - *_host entry points take HOST pointers and include the H2D/D2H copies; *_dev take DEVICE pointers and a
+ *     cudaStream_t (passed as void*) and are asynchronous.
+ *   - a cab_net is not thread-safe for mutation (train/dropout/set_weights); eval entry points may be called
+ *     concurrently from many host threads on one net (mcts_network/tree.cpp:185 does exactly that).
+ */
+#ifndef CHESSAI_B200_H_
+#define CHESSAI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CAB_API __attribute__((visibility("default")))
+#else
+#define CAB_API
+#endif
+
+#define CAB_OK 0
+#define CAB_EINVAL 1    /* bad argument (null pointer, bad dims, code outside [-9,9] is NOT checked on device) */
+#define CAB_ENODEVICE 2 /* no CUDA device / driver: the product has no CPU fallback */
+#define CAB_ECUDA 3     /* a CUDA runtime call failed; see cab_last_error() */
+#define CAB_EIO 4       /* file missing or malformed network_dump / case text */
+#define CAB_ENCCL 5     /* NCCL missing or a collective failed */
+#define CAB_ESTATE 6    /* call not valid in this state (e.g. dp step before cab_dp_init) */
+
+typedef struct cab_net cab_net; /* opaque: one network resident on one device */
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+CAB_API int cab_version(void);                 /* ABI version, currently 1 */
+CAB_API const char *cab_last_error(void);      /* thread-local message of the last failing call */
+CAB_API int cab_device_count(int *count);
+
+/* ---- network lifetime (network::Network ctors, clone)   network.cpp:37-79,155-208 ---------------------------- */
+/* dims are normalised like Network(std::vector<int>) (network.cpp:39-56): 64 prepended / 1 appended when missing;
+ * an empty or <=2-layer result yields the default {64,144,225,100,1}. Weights start at zero (uniformNetwork). */
+CAB_API int cab_net_create(const int *dims, int n_dims, int device, cab_net **out);
+CAB_API int cab_net_destroy(cab_net *net);
+CAB_API int cab_net_clone(const cab_net *net, cab_net **out);               /* Network::clone  network.cpp:195-208 */
+CAB_API int cab_net_num_layers(const cab_net *net, int *n_layers);
+CAB_API int cab_net_dims(const cab_net *net, int *dims_out);                /* n_layers ints */
+CAB_API int cab_net_num_weights(const cab_net *net, long *n_weights);
+CAB_API int cab_net_device(const cab_net *net, int *device);
+
+/* ---- weights -------------------------------------------------------------------------------------------------- */
+CAB_API int cab_net_set_weights(cab_net *net, const double *w_host, long n);  /* flat n,i,j */
+CAB_API int cab_net_get_weights(const cab_net *net, double *w_host, long n);
+/* Network::randomNetwork (network.cpp:167-173): U(-1,1). The reference draws from a sequential std::mt19937; here
+ * weight w is Philox4x32-10(key = seed, counter = (w, stream)) so the result is order- and device-independent. */
+CAB_API int cab_net_randomize(cab_net *net, uint64_t seed, uint64_t stream);
+CAB_API int cab_net_zero(cab_net *net);                                        /* Network::uniformNetwork  network.cpp:187-193 */
+
+/* ---- network_dump text format (operator>> / operator<<  network.cpp:386-426, loadFromFile :210-220) ----------- */
+/* Reads any dims (the reference's own reader only survives default-shaped files). */
+CAB_API int cab_net_load_text(const char *path, int device, cab_net **out);
+/* Byte-exact writer: "<L>\n<d0> ... <dL-1>\n" + "%.17e " per weight, no trailing newline (string_util.cpp:39-43). */
+CAB_API int cab_net_dump_text(const cab_net *net, const char *path);
+
+/* ---- encoder (Network::loadBoard + Piece::code  network.cpp:119-123) ------------------------------------------ */
+CAB_API int cab_encode_host(int device, const uint8_t *records_host, long n_boards, int8_t *codes_host);
+CAB_API int cab_encode_dev(const uint8_t *records_dev, long n_boards, int8_t *codes_dev, void *stream);
+
+/* ---- forward (Network::predictPosition  network.cpp:92-117), fp64 reference-precision path --------------------- */
+CAB_API int cab_eval_host(cab_net *net, const int8_t *codes_host, long n_boards, double *out_host);
+CAB_API int cab_eval_dev(cab_net *net, const int8_t *codes_dev, long n_boards, double *out_dev, void *stream);
+/* encoder fused in front: piece records in, evaluations out */
+CAB_API int cab_eval_records_host(cab_net *net, const uint8_t *records_host, long n_boards, double *out_host);
+/* forward that also returns every layer's activations (Network::propagate_for_training  network.cpp:139-153):
+ * acts_host receives n_boards * sum(dims[1..]) doubles, board-major, layers concatenated in order. */
+CAB_API int cab_forward_full_host(cab_net *net, const int8_t *codes_host, long n_boards, double *acts_host);
+
+/* ---- training (network::Optimizer  network.cpp:223-292, train loop main/network/train.cpp:39-68) ---------------- */
+/* Optimizer::optimize on ONE case: forward, backprop with in-place update (step lambda), re-forward, accept
+ * (lambda *= rate while lambda < max_const) or reject (lambda /= rate and roll the update back). */
+CAB_API int cab_train_case(cab_net *net, const int8_t *codes64_host, double target, double *lambda, double max_const,
+                   double rate, int *accepted, double *err, double *new_err);
+/* train_network's loop body over n cases in the given order, on the device in one launch sequence: optimize, then
+ * if lambda leaves [1e-4, 10]: lambda = 2.0 and dropout(rate 0.01) with Philox(seed, offset = reset index).
+ * accepted_host (optional) receives n flags; resets (optional) the number of lambda resets. */
+CAB_API int cab_train_sequence(cab_net *net, const int8_t *codes_host, const double *targets_host, long n_cases,
+                       double *lambda, uint64_t dropout_seed, uint8_t *accepted_host, int *resets);
+/* Minibatch extension of optimize (no reference counterpart for B > 1; reduces to it at B == 1): dW is the batch
+ * MEAN of the per-sample updates, E and E' are batch means, one accept/reject per step. With cab_dp_init the sums
+ * are all-reduced over ranks first, so every rank takes the identical decision and update. */
+CAB_API int cab_train_batch_host(cab_net *net, const int8_t *codes_host, const double *targets_host, long n_cases,
+                         double *lambda, double max_const, double rate, int *accepted, double *err, double *new_err);
+CAB_API int cab_train_batch_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases,
+                        double *lambda, double max_const, double rate, int *accepted, double *err, double *new_err,
+                        void *stream);
+/* Optimizer::dropout ("weak dilution", network.cpp:281-292): each weight w.p. rate -> U(-1,1), Philox(seed, offset). */
+CAB_API int cab_dropout(cab_net *net, double rate, uint64_t seed, uint64_t offset, long *hits);
+
+/* ---- data-parallel training: one process per GPU, NCCL all-reduce of (sum dW, sum E, sum E') ------------------- */
+CAB_API int cab_dp_unique_id(void *id128_out);                                   /* rank 0: ncclGetUniqueId (128 bytes) */
+CAB_API int cab_dp_init(cab_net *net, const void *id128, int rank, int world);   /* ncclCommInitRank on the net's device */
+CAB_API int cab_dp_shutdown(cab_net *net);
+/* raw device pointers of the gradient / scalar buffers, for callers that run their own collective
+ * (e.g. torch.distributed): grad has n_weights doubles followed by 2 doubles (sum E, sum E') and 1 count. */
+CAB_API int cab_grad_buffer(cab_net *net, double **grad_dev, long *n_doubles);
+
+/* ---- measurement helpers ---------------------------------------------------------------------------------------- */
+/* kind 0: fp64 tensor pipe (DMMA m8n8k4), 1: fp64 FMA pipe, 2: fp32 FMA pipe. Best of 10, CUDA events. */
+CAB_API int cab_measure_pipe_peak(int device, int kind, double *tflops);
+/* number of kernels this library has launched on behalf of `net` since creation (bench.py's gpu_launches) */
+CAB_API int cab_net_launch_count(const cab_net *net, long *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHESSAI_B200_H_ */

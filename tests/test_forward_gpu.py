@@ -1,0 +1,177 @@
+"""GPU parity of the forward path (K0 encoder, K1 forward, K2 forward-with-activations) through the C ABI,
+against the pinned oracle and the golden vectors produced by the reference's own code.
+
+Tolerance (BASELINE.json north_star): 1e-5 RELATIVE on the reference-precision (fp64) path. The absolute floor
+1e-12 only guards outputs that are numerically zero; the smallest golden |y| is 3.4e-7.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DEFAULT_DIMS, GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def net(cab, golden):
+    return cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"])
+
+
+def test_library_reports_device(cab):
+    assert cab.device_count() >= 1
+
+
+def test_encoder_all_codes_bit_exact(cab, port):
+    # every (type, colour, flag) combination incl. flags on pieces that ignore them and junk values
+    recs = np.zeros((4, 64, 3), dtype=np.uint8)
+    i = 0
+    for t in range(8):
+        for c in range(4):
+            for f in range(2):
+                recs.reshape(-1, 3)[i] = (t, c, f)
+                i += 1
+    got = cab.encode_records(recs)
+    want = port.encode_records(recs)
+    assert np.array_equal(got, want)
+    assert set(np.unique(got)) == set(range(-9, 10))
+
+
+def test_encoder_random_boards_bit_exact(cab, port, golden):
+    from importlib import import_module
+    synth = import_module("chess-ai_b200.synth")
+    recs = synth.codes_to_records(golden["syn_codes"])
+    assert np.array_equal(cab.encode_records(recs), golden["syn_codes"])
+    assert np.array_equal(port.encode_records(recs), golden["syn_codes"])
+
+
+def test_forward_66_cases_vs_reference_golden(net, golden):
+    y = net.predict_batch(golden["case_codes"])
+    assert rel_err(y, golden["case_forward"]).max() < RTOL
+
+
+def test_forward_synthetic_vs_reference_golden(net, golden):
+    y = net.predict_batch(golden["syn_codes"])
+    assert rel_err(y, golden["syn_forward_latest"]).max() < RTOL
+
+
+def test_forward_single_board_and_ragged_batches(net, golden):
+    codes, want = golden["syn_codes"], golden["syn_forward_latest"]
+    assert net.predict_batch(codes[:0]).shape == (0,)
+    for n in (1, 7, 8, 9, 31, 32, 33, 255, 1000):
+        y = net.predict_batch(codes[:n])
+        assert rel_err(y, want[:n]).max() < RTOL, n
+    assert abs(net.predictPosition(codes[3]) - want[3]) <= RTOL * abs(want[3])
+
+
+def test_forward_records_path_matches_codes_path(cab, net, golden):
+    from importlib import import_module
+    synth = import_module("chess-ai_b200.synth")
+    recs = synth.codes_to_records(golden["syn_codes"][:300])
+    assert np.array_equal(net.predict_records(recs), net.predict_batch(golden["syn_codes"][:300]))
+    b = cab.Board(recs[5])
+    assert net.predictPosition(b) == net.predict_batch(golden["syn_codes"][5:6])[0]
+
+
+def test_forward_random_default_net_vs_oracle(cab, port, golden):
+    # weights = Network::randomNetwork() of the reference in a fresh process (golden sample pins the stream)
+    mt = port.mt_new()
+    pn = port.random_net(DEFAULT_DIMS, mt)
+    w = pn.get_weights()
+    assert np.array_equal(w[::101], golden["random_default_weights_sample"])
+    net = cab.Network.from_weights(DEFAULT_DIMS, w)
+    y = net.predict_batch(golden["syn_codes"][:512])
+    assert rel_err(y, golden["syn_forward_random"]).max() < RTOL
+
+
+def test_forward_small_dims_vs_reference_golden(cab, golden):
+    dims = golden["json"]["random_small_dims"]
+    net = cab.Network.from_weights(dims, golden["random_small_weights"])
+    assert net.dims == dims
+    y = net.predict_batch(golden["syn_codes"][:512])
+    assert rel_err(y, golden["syn_forward_small"]).max() < RTOL
+
+
+@pytest.mark.parametrize("dims", [[64, 8, 1], [64, 300, 1], [64, 17, 33, 9, 5, 1], [64, 264, 40, 1], [64, 520, 1]])
+def test_forward_odd_shapes_vs_oracle(cab, port, golden, dims):
+    # widths that are not multiples of 8, more than 32 output tiles (n-block split, ping-pong buffers), deep nets
+    rng = np.random.default_rng(sum(dims))
+    pn = port.new_net(dims)
+    w = rng.uniform(-1, 1, pn.num_weights)
+    pn.set_weights(w)
+    net = cab.Network.from_weights(dims, w)
+    codes = golden["syn_codes"][:200]
+    assert rel_err(net.predict_batch(codes), pn.predict(codes)).max() < RTOL
+
+
+def test_forward_full_matches_oracle_activations(cab, port, net, golden):
+    pn = port.net_from_weights(DEFAULT_DIMS, golden["latest_weights"])
+    codes = golden["syn_codes"][:40]
+    acts = net.forward_full(codes)
+    for b in range(len(codes)):
+        ne, _ = pn.forward_full(codes[b])
+        want = ne[64:]
+        assert np.abs(acts[b] - want).max() < 1e-9  # activations live in (-4, 4)
+
+
+def test_saturated_inputs_give_exact_bounds(cab):
+    # exp overflow -> exactly +-4: huge weights drive every unit into saturation, no NaN
+    dims = [64, 16, 1]
+    net = cab.Network(dims)
+    w = np.full(net.num_weights, 1e6)
+    net.set_weights(w)
+    codes = np.full((8, 64), 9, dtype=np.int8)
+    codes[4:] = -9
+    y = net.predict_batch(codes)
+    assert np.array_equal(y, np.array([4.0] * 4 + [-4.0] * 4))
+
+
+def test_dump_is_byte_exact_and_reloads(cab, net, golden, tmp_path, port):
+    p = str(tmp_path / "latest.txt")
+    net.dump(p)
+    j = golden["json"]["latest_txt"]
+    assert os.path.getsize(p) == j["bytes"]
+    import hashlib
+    assert hashlib.sha256(open(p, "rb").read()).hexdigest() == j["sha256"]
+    again = cab.Network.loadFromFile(p)
+    assert again.dims == DEFAULT_DIMS
+    assert np.array_equal(again.get_weights(), golden["latest_weights"])
+
+
+def test_clone_is_deep(cab, net, golden):
+    c = net.clone()
+    assert np.array_equal(c.get_weights(), net.get_weights())
+    c.set_weights(np.zeros(c.num_weights))
+    assert np.array_equal(net.get_weights(), golden["latest_weights"])
+    assert np.all(c.predict_batch(golden["syn_codes"][:16]) == 0.0)
+
+
+def test_large_batch_properties(cab, net, golden):
+    # 200k boards (several host<->device chunks): permutation-equivariance and agreement with the small-batch path
+    from importlib import import_module
+    codes = import_module("chess-ai_b200").synthetic_boards(200_000)
+    y = net.predict_batch(codes)
+    assert np.all(np.isfinite(y)) and np.abs(y).max() < 4.0 + 1e-12
+    assert rel_err(y[:2048], golden["syn_forward_latest"]).max() < RTOL
+    perm = np.random.default_rng(1).permutation(len(codes))
+    y2 = net.predict_batch(codes[perm])
+    assert np.array_equal(y2, y[perm])
+
+
+def test_concurrent_eval_from_threads(cab, net, golden):
+    import threading
+    codes, want = golden["syn_codes"], golden["syn_forward_latest"]
+    errs = []
+
+    def work(i):
+        for _ in range(5):
+            y = net.predict_batch(codes[i * 100:(i + 3) * 100])
+            if rel_err(y, want[i * 100:(i + 3) * 100]).max() >= RTOL:
+                errs.append(i)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
