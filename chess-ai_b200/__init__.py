@@ -60,6 +60,7 @@ _SIGS = {
     "cab_encode_dev": [_vp, C.c_long, _vp, _vp],
     "cab_eval_host": [_vp, _vp, C.c_long, _vp],
     "cab_eval_dev": [_vp, _vp, C.c_long, _vp, _vp],
+    "cab_eval_dev_batches": [_vp, _vp, C.c_long, C.c_long, _vp, C.POINTER(_vp), C.c_int],
     "cab_eval_records_host": [_vp, _u8p, C.c_long, _f64p],
     "cab_forward_full_host": [_vp, _i8p, C.c_long, _f64p],
     "cab_train_case": [_vp, _i8p, C.c_double, _dp, C.c_double, C.c_double, _ip, _dp, _dp],
@@ -305,6 +306,11 @@ class Network:
     def eval_dev_ptr(self, codes_dev_ptr, n, out_dev_ptr, stream=0):
         """Asynchronous evaluation on device pointers (codes int8 [n,64], out fp64 [n]) on a CUDA stream."""
         _ck(lib().cab_eval_dev(self._h, codes_dev_ptr, n, out_dev_ptr, stream))
+
+    def eval_dev_batches(self, codes_dev_ptr, n, batch, out_dev_ptr, streams):
+        """ceil(n/batch) asynchronous launches of `batch` boards, round-robin over the given cudaStream_t handles."""
+        arr = (_vp * len(streams))(*streams)
+        _ck(lib().cab_eval_dev_batches(self._h, codes_dev_ptr, n, batch, out_dev_ptr, arr, len(streams)))
 
     def forward_full(self, codes):
         """Network::propagate_for_training (network.cpp:139-153): activations of every layer, [B, sum(dims[1:])]."""

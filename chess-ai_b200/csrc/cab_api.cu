@@ -220,8 +220,15 @@ static void free_plan(StreamPlan *plan) {
   plan->d_chunks = nullptr; plan->d_segs = nullptr; plan->d_pack = nullptr;
 }
 
-size_t forward_smem_bytes(int a_units) {
-  return (size_t) kStages * kStageBytes + (size_t) kConsumerWarps * a_units * kUnitBytes + 2 * kStages * sizeof(uint64_t);
+size_t forward_smem_bytes(int a_units, int n_cons) {
+  return (size_t) kStages * kStageBytes + (size_t) n_cons * a_units * kUnitBytes + 2 * kStages * sizeof(uint64_t);
+}
+
+// consumer warps per CTA: as many as fit (<= kConsumerWarps); wide layers trade warps for activation space
+int consumer_warps_for(int a_units) {
+  for (int w = kConsumerWarps; w >= 1; --w)
+    if (forward_smem_bytes(a_units, w) <= 227 * 1024) return w;
+  return 0;
 }
 
 // (re)build the packed streams from d_w on `stream`
@@ -247,23 +254,30 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
   a.n_chunks = (int) net->fwd.chunks.size();
   a.a_units = net->fwd.a_units;
   a.n_boards = n_boards;
-  a.n_groups = (n_boards + kBoardsPerCta - 1) / kBoardsPerCta;
+  const int n_cons = consumer_warps_for(a.a_units);
+  const int boards_per_cta = n_cons * kBoardsPerWarp;
+  a.n_groups = (n_boards + boards_per_cta - 1) / boards_per_cta;
   a.codes = d_codes;
   a.out = d_out;
   a.save = d_save;
   a.save_stride = save_stride;
-  const size_t smem = forward_smem_bytes(a.a_units);
+  const size_t smem = forward_smem_bytes(a.a_units, n_cons);
   const int per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
   const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * per_sm);
-  mlp_forward_kernel<<<grid, kThreads, smem, stream>>>(a);
+  mlp_forward_kernel<<<grid, (n_cons + 1) * 32, smem, stream>>>(a);
   net->launches++;
   CAB_CUDA(cudaGetLastError());
   return CAB_OK;
 }
 
 static int select_device(int device) {
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
+  static std::atomic<int> cached_count{-1};
+  int n = cached_count.load();
+  cudaError_t e = cudaSuccess;
+  if (n <= 0) {
+    e = cudaGetDeviceCount(&n);
+    if (e == cudaSuccess && n > 0) cached_count.store(n);
+  }
   if (e != cudaSuccess || n == 0) {
     set_error("no CUDA device available (%s): libchessai_b200 has no CPU fallback", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
     return CAB_ENODEVICE;
@@ -315,9 +329,9 @@ static int create_exact(const std::vector<int> &dims, int device, cab_net **out)
   build_plan(net, true, &net->bwd);
   if ((rc = upload_plan(&net->fwd)) != CAB_OK) return rc;
   if ((rc = upload_plan(&net->bwd)) != CAB_OK) return rc;
-  const size_t smem = forward_smem_bytes(std::max(net->fwd.a_units, net->bwd.a_units));
-  if (smem > 227 * 1024) {
-    set_error("layer too wide for the fp64 stream kernel: needs %zu B shared memory", smem);
+  if (consumer_warps_for(std::max(net->fwd.a_units, net->bwd.a_units)) == 0) {
+    set_error("layer too wide for the fp64 stream kernel: %d activation units per warp do not fit shared memory",
+              std::max(net->fwd.a_units, net->bwd.a_units));
     delete net;
     return CAB_EINVAL;
   }
@@ -607,6 +621,31 @@ int cab_eval_dev(cab_net *net, const int8_t *codes_dev, long n, double *out_dev,
     }
   }
   return launch_forward(net, codes_dev, n, out_dev, nullptr, 0, (cudaStream_t) stream);
+}
+
+int cab_eval_dev_batches(cab_net *net, const int8_t *codes_dev, long n, long batch, double *out_dev,
+                         void *const *streams, int n_streams) {
+  if (!net || n < 0 || batch <= 0 || n_streams <= 0 || !streams || (n > 0 && (!codes_dev || !out_dev))) {
+    set_error("bad argument");
+    return CAB_EINVAL;
+  }
+  int rc = select_device(net->device);
+  if (rc != CAB_OK) return rc;
+  {
+    std::lock_guard<std::mutex> lk(net->mu);
+    if (net->pack_dirty) {
+      rc = ensure_packed(net, (cudaStream_t) streams[0]);
+      if (rc != CAB_OK) return rc;
+      CAB_CUDA(cudaStreamSynchronize((cudaStream_t) streams[0]));
+    }
+  }
+  int i = 0;
+  for (long b0 = 0; b0 < n; b0 += batch, ++i) {
+    rc = launch_forward(net, codes_dev + b0 * 64, std::min(batch, n - b0), out_dev + b0, nullptr, 0,
+                        (cudaStream_t) streams[i % n_streams]);
+    if (rc != CAB_OK) return rc;
+  }
+  return CAB_OK;
 }
 
 int cab_eval_host(cab_net *net, const int8_t *codes, long n, double *out) {

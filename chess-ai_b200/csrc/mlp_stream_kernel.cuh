@@ -62,7 +62,7 @@ struct ForwardArgs {
   int n_chunks;
   int a_units;              // per-warp activation buffer, in units
   long n_boards;
-  long n_groups;            // ceil(n_boards / 32)
+  long n_groups;            // ceil(n_boards / (8 * consumer warps))
   const int8_t *codes;      // [n_boards][64]
   double *out;              // [n_boards] or nullptr
   double *save;             // saved activations in unit layout, or nullptr (K2: propagate_for_training)
@@ -74,20 +74,21 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_forward_kernel(const ForwardA
   uint8_t *ring = smem;
   double2 *abuf_all = reinterpret_cast<double2 *>(smem + kStages * kStageBytes);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes +
-                                                (size_t) kConsumerWarps * args.a_units * kUnitBytes);
+                                                (size_t) ((blockDim.x >> 5) - 1) * args.a_units * kUnitBytes);
   uint64_t *empty = full + kStages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cons = (int) (blockDim.x >> 5) - 1;  // consumer warps in this launch (<= kConsumerWarps)
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kConsumerWarps);
+      mbar_init(&empty[s], n_cons);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == kConsumerWarps) {
+  if (warp == n_cons) {
     // ---------------- producer: stream the packed weights into the ring, once per board group ----------------
     if (lane == 0) {
       uint32_t cc = 0;
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_forward_kernel(const ForwardA
   uint32_t cc = 0;
 
   for (long g = blockIdx.x; g < args.n_groups; g += gridDim.x) {
-    const long board0 = (g * kConsumerWarps + warp) * kBoardsPerWarp;
+    const long board0 = (g * n_cons + warp) * kBoardsPerWarp;
     const long board = board0 + m;
     const bool valid = board < args.n_boards;
 

@@ -84,6 +84,10 @@ CAB_API int cab_encode_dev(const uint8_t *records_dev, long n_boards, int8_t *co
 /* ---- forward (Network::predictPosition  network.cpp:92-117), fp64 reference-precision path --------------------- */
 CAB_API int cab_eval_host(cab_net *net, const int8_t *codes_host, long n_boards, double *out_host);
 CAB_API int cab_eval_dev(cab_net *net, const int8_t *codes_dev, long n_boards, double *out_dev, void *stream);
+/* The leaf-queue shape: n boards already on the device, evaluated as ceil(n/batch) launches of `batch` boards issued
+ * round-robin over the caller's streams (cudaStream_t[n_streams]) so consecutive launches overlap. Asynchronous. */
+CAB_API int cab_eval_dev_batches(cab_net *net, const int8_t *codes_dev, long n_boards, long batch, double *out_dev,
+                                 void *const *streams, int n_streams);
 /* encoder fused in front: piece records in, evaluations out */
 CAB_API int cab_eval_records_host(cab_net *net, const uint8_t *records_host, long n_boards, double *out_host);
 /* forward that also returns every layer's activations (Network::propagate_for_training  network.cpp:139-153):

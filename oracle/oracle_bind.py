@@ -287,10 +287,10 @@ class RefNet:
         assert self.lib.ref_predict_codes(self.ptr, c, len(c), out) == 0
         return out
 
-    def time_predict(self, codes, threads=1):
+    def time_predict(self, codes, threads=1, reps=1):
         c = _codes(codes)
         out = np.zeros(len(c), dtype=np.float64)
-        return float(self.lib.ref_time_predict(self.ptr, c, len(c), threads, out)), out
+        return float(self.lib.ref_time_predict(self.ptr, c, len(c), threads, reps, out)), out
 
     def optimize(self, code64, target, lam, max_const=15.0, rate=1.1):
         c = _codes(code64)
@@ -361,7 +361,7 @@ class RefOracle:
         L.ref_predict_codes.restype = C.c_int
         L.ref_predict_codes.argtypes = [vp, _i8p, C.c_long, _f64p]
         L.ref_time_predict.restype = C.c_double
-        L.ref_time_predict.argtypes = [vp, _i8p, C.c_long, C.c_int, _f64p]
+        L.ref_time_predict.argtypes = [vp, _i8p, C.c_long, C.c_int, C.c_int, _f64p]
         L.ref_optimize_codes.restype = C.c_int
         L.ref_optimize_codes.argtypes = [vp, _i8p, C.c_double, C.POINTER(C.c_double), C.c_double, C.c_double]
         L.ref_train_sequence.restype = C.c_int

@@ -170,7 +170,7 @@ int ref_predict_codes(void *net, const int8_t *codes, long n_boards, double *out
 
 // Timed forward over pre-built boards, `threads` host threads, one Network::clone() per thread over disjoint
 // shards (predictPosition is re-entrant, network.cpp:93-94). Returns seconds of wall time for the predict loop only.
-double ref_time_predict(void *net, const int8_t *codes, long n_boards, int threads, double *out) {
+double ref_time_predict(void *net, const int8_t *codes, long n_boards, int threads, int reps, double *out) {
   auto *n = static_cast<network::Network *>(net);
   std::vector<game::Board *> boards(n_boards);
   for (long b = 0; b < n_boards; ++b) boards[b] = board_from_codes(codes + 64 * b);
@@ -185,7 +185,8 @@ double ref_time_predict(void *net, const int8_t *codes, long n_boards, int threa
       long lo = n_boards * t / threads, hi = n_boards * (t + 1) / threads;
       ready.fetch_add(1);
       while (!go.load()) {}
-      for (long b = lo; b < hi; ++b) out[b] = nets[t]->predictPosition(boards[b]);
+      for (int r = 0; r < reps; ++r)
+        for (long b = lo; b < hi; ++b) out[b] = nets[t]->predictPosition(boards[b]);
     });
   while (ready.load() < threads) {}
   auto t0 = std::chrono::steady_clock::now();
