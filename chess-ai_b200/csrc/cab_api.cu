@@ -194,7 +194,8 @@ static void build_plan(const cab_net *net, bool transposed, StreamPlan *plan) {
         d.layer = (uint16_t) l;
         d.n_tiles = (uint16_t) n_tiles;
         d.save_off = transposed ? net->act_unit_off[l] : net->act_unit_off[l + 1];
-        d.n_real = (uint32_t) out_w;
+        d.save_in = transposed ? net->act_unit_off[l + 1] : net->act_unit_off[l];
+        if (!transposed && l > 0 && b == 0) d.flags |= kActIn;  // first n-block activates (and writes back) its input
         plan->chunks.push_back(d);
       }
       off += sg.n_doubles;
@@ -220,16 +221,35 @@ static void free_plan(StreamPlan *plan) {
   plan->d_chunks = nullptr; plan->d_segs = nullptr; plan->d_pack = nullptr;
 }
 
-size_t forward_smem_bytes(int a_units, int n_cons) {
-  return (size_t) kStages * kStageBytes + (size_t) n_cons * a_units * kUnitBytes + 2 * kStages * sizeof(uint64_t);
+size_t forward_smem_bytes(int a_units, int n_cons, int n_stages) {
+  return fwd_smem_ring(n_stages) + fwd_smem_abuf(n_cons, a_units) + fwd_smem_tail(n_stages);
 }
 
-// consumer warps per CTA: as many as fit (<= kConsumerWarps); wide layers trade warps for activation space
-int consumer_warps_for(int a_units) {
-  for (int w = kConsumerWarps; w >= 1; --w)
-    if (forward_smem_bytes(a_units, w) <= 227 * 1024) return w;
-  return 0;
+constexpr size_t kSmemMax = 227 * 1024;
+
+// CTA geometry: warp PAIRS per CTA (8 boards each), weight-ring depth, CTAs per SM. Wide layers trade pairs for
+// activation space. n_cons counts pairs. CAB_FWD_PAIRS / CAB_FWD_STAGES override for experiments.
+struct Geometry { int n_cons, n_stages, ctas_per_sm; };
+Geometry choose_geometry(int a_units, long n_boards, int sm_count) {
+  static const int env_w = getenv("CAB_FWD_PAIRS") ? atoi(getenv("CAB_FWD_PAIRS")) : 0;
+  static const int env_s = getenv("CAB_FWD_STAGES") ? atoi(getenv("CAB_FWD_STAGES")) : 0;
+  (void) n_boards; (void) sm_count;
+  Geometry g{0, 0, 1};
+  const int max_pairs = kConsumerWarps / 2;
+  const int want = env_w > 0 ? std::min(env_w, max_pairs) : max_pairs;
+  for (int p = want; p >= 1; --p) {
+    if (forward_smem_bytes(a_units, p, 2) > kSmemMax) continue;
+    g.n_cons = p;
+    int st = env_s > 0 ? std::min(env_s, kMaxStages) : 4;
+    while (st > 2 && forward_smem_bytes(a_units, p, st) > kSmemMax) --st;
+    g.n_stages = st;
+    // two CTAs per SM only when both fit and together keep <= 16 warps
+    g.ctas_per_sm = (p <= max_pairs / 2 && (forward_smem_bytes(a_units, p, st) + 1024) * 2 <= kSmemMax) ? 2 : 1;
+    return g;
+  }
+  return g;
 }
+int consumer_warps_for(int a_units) { return choose_geometry(a_units, 0, 148).n_cons; }
 
 // (re)build the packed streams from d_w on `stream`
 int ensure_packed(cab_net *net, cudaStream_t stream) {
@@ -254,17 +274,40 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
   a.n_chunks = (int) net->fwd.chunks.size();
   a.a_units = net->fwd.a_units;
   a.n_boards = n_boards;
-  const int n_cons = consumer_warps_for(a.a_units);
+  const Geometry geo = choose_geometry(a.a_units, n_boards, net->sm_count);
+  const int n_cons = geo.n_cons;
+  a.n_stages = geo.n_stages;
   const int boards_per_cta = n_cons * kBoardsPerWarp;
   a.n_groups = (n_boards + boards_per_cta - 1) / boards_per_cta;
   a.codes = d_codes;
   a.out = d_out;
   a.save = d_save;
   a.save_stride = save_stride;
-  const size_t smem = forward_smem_bytes(a.a_units, n_cons);
-  const int per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
-  const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * per_sm);
-  mlp_forward_kernel<<<grid, (n_cons + 1) * 32, smem, stream>>>(a);
+  const size_t smem = forward_smem_bytes(a.a_units, n_cons, geo.n_stages);
+  const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * geo.ctas_per_sm);
+  static const bool prof_env = getenv("CAB_FWD_PROFILE") != nullptr;
+  if (prof_env) {
+    // debug: per-warp phase cycle counters of ONE launch, printed to stderr (never on by default)
+    long long *d_prof = nullptr;
+    const long nw = (long) grid * n_cons * 2;
+    CAB_CUDA(cudaMalloc(&d_prof, nw * 8 * sizeof(long long)));
+    CAB_CUDA(cudaMemset(d_prof, 0, nw * 8 * sizeof(long long)));
+    a.prof = d_prof;
+    CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    mlp_forward_kernel<true><<<grid, n_cons * 64, smem, stream>>>(a);
+    CAB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<long long> h(nw * 8);
+    CAB_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_prof);
+    double sum[8] = {0};
+    for (long w = 0; w < nw; ++w) for (int i = 0; i < 8; ++i) sum[i] += (double) h[w * 8 + i];
+    fprintf(stderr, "[cab profile] boards=%ld grid=%d pairs/cta=%d stages=%d  avg cycles per warp: load=%.0f desc=%.0f wait_full=%.0f "
+            "mma=%.0f refill=%.0f act=%.0f total=%.0f\n", n_boards, grid, n_cons, geo.n_stages, sum[0] / nw, sum[1] / nw, sum[2] / nw,
+            sum[3] / nw, sum[4] / nw, sum[5] / nw, sum[6] / nw);
+    net->launches++;
+    return CAB_OK;
+  }
+  mlp_forward_kernel<false><<<grid, n_cons * 64, smem, stream>>>(a);
   net->launches++;
   CAB_CUDA(cudaGetLastError());
   return CAB_OK;
@@ -335,7 +378,7 @@ static int create_exact(const std::vector<int> &dims, int device, cab_net **out)
     delete net;
     return CAB_EINVAL;
   }
-  CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   net->pack_dirty = true;
   *out = net;
   return CAB_OK;
@@ -665,7 +708,7 @@ int cab_forward_full_host(cab_net *net, const int8_t *codes, long n, double *act
   if (n == 0) return CAB_OK;
   int rc = select_device(net->device);
   if (rc != CAB_OK) return rc;
-  const long pad = (n + kBoardsPerCta - 1) / kBoardsPerCta * kBoardsPerCta;
+  const long pad = (n + 63) / 64 * 64;
   const long stride = pad * 8;
   int8_t *d_codes = nullptr;
   double *d_save = nullptr, *d_out = nullptr;

@@ -21,16 +21,16 @@
 
 namespace cab {
 
-constexpr int kConsumerWarps = 4;                       // warps doing DMMA; each owns 8 boards
-constexpr int kThreads = (kConsumerWarps + 1) * 32;     // + 1 producer warp issuing bulk copies
-constexpr int kBoardsPerWarp = 8;
-constexpr int kBoardsPerCta = kConsumerWarps * kBoardsPerWarp;
-constexpr int kStages = 3;                              // weight ring depth
-constexpr int kStageBytes = 16384;                      // one ring slot
-constexpr int kMaxNB = 32;                              // output tiles accumulated in registers at once
+constexpr int kConsumerWarps = 16;                      // max warps per CTA; a PAIR of warps owns 8 boards
+constexpr int kMaxThreads = kConsumerWarps * 32;        // no producer warp: the last warp off a ring slot re-arms it
+constexpr int kBoardsPerWarp = 8;                       // boards per warp pair (one DMMA M tile)
+constexpr int kMaxStages = 8;                           // weight ring depth upper bound
+constexpr int kStageBytes = 32768;                      // one ring slot
+constexpr int kMaxNB = 32;                              // output tiles of one n-block (split over the pair)
+constexpr int kMaxNBH = 16;                             // output tiles one warp accumulates in registers
 constexpr int kUnitBytes = 512;                         // 32 lanes x double2
 
-enum ChunkFlags : uint8_t { kFirst = 1, kLast = 2, kFinal = 4 };
+enum ChunkFlags : uint8_t { kFirst = 1, kLast = 2, kFinal = 4, kActIn = 8 };  // kActIn: apply f() to the A operand on load
 
 struct __align__(16) ChunkDesc {
   uint32_t src_off;  // byte offset into the packed stream
@@ -45,7 +45,7 @@ struct __align__(16) ChunkDesc {
   uint16_t layer;    // weight layer index (0-based)
   uint16_t n_tiles;  // output tiles of the whole layer
   uint32_t save_off; // unit offset of this layer's output inside the saved-activation tensor (x n_boards_pad)
-  uint32_t n_real;   // real (unpadded) output width of the layer
+  uint32_t save_in;  // unit offset of this layer's INPUT activations inside the saved-activation tensor
 };
 static_assert(sizeof(ChunkDesc) == 32, "ChunkDesc must stay 32 bytes");
 
@@ -167,7 +167,51 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 
 // The reference activation, as written (mcts_network/network.h:83-94):
 //   f(x) = MAX * modifiedSigmoid(x / WIDTH),  modifiedSigmoid(u) = 2/(1+exp(-2u)) - 1,  MAX = WIDTH = 4
-__device__ __forceinline__ double act_f(double x) { return 4.0 * (2.0 / (1.0 + exp(-2.0 * (x / 4.0))) - 1.0); }
+__device__ __forceinline__ double act_f_libm(double x) { return 4.0 * (2.0 / (1.0 + exp(-2.0 * (x / 4.0))) - 1.0); }
+
+// Same expression, same operation order, but exp and the division are branch-free so 8 of them pipeline per lane:
+//   t = -2*(x/4) (exact), clamped to +-60: beyond that 1+e rounds to e or 1 and the reference's inf / 0 path and this one
+//       both give exactly -+4
+//   e = exp(t) = 2^n * P(r), n = rint(t*log2 e), r = t - n*ln2 (Cody-Waite), P = degree-13 Taylor (|r| <= 0.347:
+//       truncation 4e-18 relative), scaled by adding n to the exponent field (|n| <= 87, result normal)
+//   1/(1+e): MUFU.RCP64H seed + 3 Newton steps (error squares each step from ~2^-20)
+//   f = 4*(2/(1+e) - 1) = fma(8, 1/(1+e), -4)  (the *4 is exact, so one rounding either way)
+// Differences from libm-based evaluation are O(1 ulp) of the intermediate e, i.e. <= ~5e-16 absolute on f.
+__device__ __forceinline__ double act_f(double x) {
+  double t = -0.5 * x;
+  t = fmin(fmax(t, -60.0), 60.0);
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to nearest integer in the low bits
+  const double nm = fma(t, 1.4426950408889634, magic);
+  const double nd = nm - magic;
+  double r = fma(nd, -6.93147180369123816490e-01, t);
+  r = fma(nd, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;            // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int n = __double2loint(nm);             // low word of the magic sum holds the integer
+  const double e = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  const double d = 1.0 + e;
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double err = fma(-d, y, 1.0);
+  y = fma(y, err, y);
+  err = fma(-d, y, 1.0);
+  y = fma(y, err, y);
+  err = fma(-d, y, 1.0);
+  y = fma(y, err, y);
+  return fma(8.0, y, -4.0);
+}
 // f'(x) = MAX * (1 - sig^2) / WIDTH with sig = modifiedSigmoid(x/WIDTH) = f(x)/MAX, so it is a function of a = f(x):
 __device__ __forceinline__ double act_df_from_a(double a) {
   const double sig = a / 4.0;

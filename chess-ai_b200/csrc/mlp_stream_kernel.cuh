@@ -3,163 +3,285 @@
 // Replaces Network::predictPosition / propagate_for_training (/root/reference/src/mcts_network/network.cpp:92-153):
 //   per layer, per output j:  sum_i a[i] * W[i][j]  ->  f(sum)
 // B200 design:
-//   * one warp owns 8 boards through ALL layers; activations never leave its private shared-memory units
+//   * a PAIR of warps owns 8 boards through ALL layers; each warp of the pair computes half of every layer's output
+//     tiles. Halving the accumulators keeps a thread under 128 registers, so 16 warps (4 per SMSP) are resident and
+//     one warp's loads / barriers / activation math hide behind the others' DMMAs. The pair shares one activation
+//     buffer in shared memory (8 boards x widest layer) and meets at a 64-thread named barrier per layer boundary
 //   * the matmuls run on the fp64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), accumulators in registers
 //   * weights arrive as a pre-packed B-fragment stream, moved L2 -> shared by 1-D TMA bulk copies
-//     (cp.async.bulk, SASS UBLKCP) issued by a producer warp into a 3-slot mbarrier ring shared by the CTA
+//     (cp.async.bulk, SASS UBLKCP) into an mbarrier ring shared by the CTA. No producer warp: the LAST warp to
+//     finish a chunk (shared-memory arrival counter) re-arms that ring slot on the spot
 //   * the DMMA C-fragment of tile j IS the A-fragment pair of the next layer's k-steps (2j, 2j+1) under the feature
-//     permutation k = 8t + 2q + h that the packed stream bakes in, so there is no transpose, no __syncthreads and
-//     no inter-warp traffic between layers
-//   * persistent grid: CTAs loop over 32-board groups; the weight stream is re-read from L2 per group
+//     permutation k = 8t + 2q + h that the packed stream bakes in, so activations never change layout
+//   * persistent grid: CTAs loop over board groups; the weight stream is re-read from L2 per group
 #pragma once
 #include "cab_internal.cuh"
 
 namespace cab {
 
-template <int NB>
-__device__ __forceinline__ void run_chunk(double (&acc)[kMaxNB][2], const double2 *__restrict__ a_in,
-                                          const double2 *__restrict__ w, int tcount, int lane) {
-  for (int t = 0; t < tcount; ++t) {
-    const double2 a = a_in[t * 32 + lane];
-    const double2 *wt = w + (size_t) t * NB * 32 + lane;
+// shared-memory fragment load with a pinned position in the instruction stream
+__device__ __forceinline__ double2 lds_frag(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void dmma_v(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void pair_barrier(int pair) {  // named barrier 1 + pair, 64 threads (SASS BAR.SYNC)
+  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+
+// One chunk = tcount input units x NBH output tiles of this warp's half. B fragments are fetched one group of kG
+// tiles ahead (across the t boundary too); inside a group the kG ".x" DMMAs are issued before the dependent ".y" ones.
+constexpr int kG = 2;
+template <int NBH>
+__device__ __forceinline__ void run_chunk(double (&acc)[kMaxNBH][2], uint32_t a_addr, uint32_t w_addr, uint32_t t_stride,
+                                          int tcount) {
+  constexpr int NG = (NBH + kG - 1) / kG;
+  double2 bcur[kG], bnxt[kG];
+  double2 a = lds_frag(a_addr);
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const double2 b = wt[j * 32];
-      dmma884(acc[j], a.x, b.x);
-      dmma884(acc[j], a.y, b.y);
+  for (int i = 0; i < kG; ++i)
+    if (i < NBH) bcur[i] = lds_frag(w_addr + i * kUnitBytes);
+  for (int t = 0; t < tcount; ++t) {
+    const uint32_t wt = w_addr + (uint32_t) t * t_stride;
+    const bool more = t + 1 < tcount;
+    double2 a_next = a;
+    if (more) a_next = lds_frag(a_addr + (uint32_t) (t + 1) * kUnitBytes);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      if (g + 1 < NG) {
+#pragma unroll
+        for (int i = 0; i < kG; ++i)
+          if ((g + 1) * kG + i < NBH) bnxt[i] = lds_frag(wt + ((g + 1) * kG + i) * kUnitBytes);
+      } else if (more) {
+#pragma unroll
+        for (int i = 0; i < kG; ++i)
+          if (i < NBH) bnxt[i] = lds_frag(wt + t_stride + i * kUnitBytes);
+      }
+#pragma unroll
+      for (int i = 0; i < kG; ++i)
+        if (g * kG + i < NBH) dmma_v(acc[g * kG + i], a.x, bcur[i].x);
+#pragma unroll
+      for (int i = 0; i < kG; ++i)
+        if (g * kG + i < NBH) dmma_v(acc[g * kG + i], a.y, bcur[i].y);
+#pragma unroll
+      for (int i = 0; i < kG; ++i) bcur[i] = bnxt[i];
     }
+    a = a_next;
   }
 }
 
-template <int NB>
-__device__ __forceinline__ void store_acc(const double (&acc)[kMaxNB][2], double2 *__restrict__ a_out, int lane) {
+template <int NBH>
+__device__ __forceinline__ void store_acc(const double (&acc)[kMaxNBH][2], double2 *__restrict__ a_out, int lane) {
 #pragma unroll
-  for (int j = 0; j < NB; ++j) a_out[j * 32 + lane] = make_double2(acc[j][0], acc[j][1]);
+  for (int j = 0; j < NBH; ++j) a_out[j * 32 + lane] = make_double2(acc[j][0], acc[j][1]);
 }
 
-#define CAB_NB_CASE(N)                        \
-  case N:                                     \
-    run_chunk<N>(acc, a_in, w, tcount, lane); \
-    if (last) store_acc<N>(acc, a_out, lane); \
-    break;
-
-__device__ __forceinline__ void dispatch_chunk(int nb, double (&acc)[kMaxNB][2], const double2 *a_in, const double2 *w,
-                                               int tcount, int lane, bool last, double2 *a_out) {
-  switch (nb) {
+#define CAB_NB_CASE(N) \
+  case N: run_chunk<N>(acc, a_addr, w_addr, t_stride, tcount); break;
+__device__ __forceinline__ void dispatch_chunk(int nbh, double (&acc)[kMaxNBH][2], uint32_t a_addr, uint32_t w_addr,
+                                               uint32_t t_stride, int tcount) {
+  switch (nbh) {
     CAB_NB_CASE(1) CAB_NB_CASE(2) CAB_NB_CASE(3) CAB_NB_CASE(4) CAB_NB_CASE(5) CAB_NB_CASE(6) CAB_NB_CASE(7)
     CAB_NB_CASE(8) CAB_NB_CASE(9) CAB_NB_CASE(10) CAB_NB_CASE(11) CAB_NB_CASE(12) CAB_NB_CASE(13) CAB_NB_CASE(14)
-    CAB_NB_CASE(15) CAB_NB_CASE(16) CAB_NB_CASE(17) CAB_NB_CASE(18) CAB_NB_CASE(19) CAB_NB_CASE(20) CAB_NB_CASE(21)
-    CAB_NB_CASE(22) CAB_NB_CASE(23) CAB_NB_CASE(24) CAB_NB_CASE(25) CAB_NB_CASE(26) CAB_NB_CASE(27) CAB_NB_CASE(28)
-    CAB_NB_CASE(29) CAB_NB_CASE(30) CAB_NB_CASE(31) CAB_NB_CASE(32)
+    CAB_NB_CASE(15) CAB_NB_CASE(16)
+    default: break;
+  }
+}
+#undef CAB_NB_CASE
+#define CAB_NB_CASE(N) \
+  case N: store_acc<N>(acc, a_out, lane); break;
+__device__ __forceinline__ void dispatch_store(int nbh, const double (&acc)[kMaxNBH][2], double2 *a_out, int lane) {
+  switch (nbh) {
+    CAB_NB_CASE(1) CAB_NB_CASE(2) CAB_NB_CASE(3) CAB_NB_CASE(4) CAB_NB_CASE(5) CAB_NB_CASE(6) CAB_NB_CASE(7)
+    CAB_NB_CASE(8) CAB_NB_CASE(9) CAB_NB_CASE(10) CAB_NB_CASE(11) CAB_NB_CASE(12) CAB_NB_CASE(13) CAB_NB_CASE(14)
+    CAB_NB_CASE(15) CAB_NB_CASE(16)
     default: break;
   }
 }
 #undef CAB_NB_CASE
 
+constexpr int kSmemChunks = 96;  // chunk descriptors cached in shared memory (default net: 21); longer plans read L2
+
 struct ForwardArgs {
   const uint8_t *pack;      // packed fragment stream of W
   const ChunkDesc *chunks;
   int n_chunks;
-  int a_units;              // per-warp activation buffer, in units
+  int a_units;              // per-pair activation buffer, in units
   long n_boards;
-  long n_groups;            // ceil(n_boards / (8 * consumer warps))
+  long n_groups;            // ceil(n_boards / (8 * pairs per CTA))
   const int8_t *codes;      // [n_boards][64]
   double *out;              // [n_boards] or nullptr
   double *save;             // saved activations in unit layout, or nullptr (K2: propagate_for_training)
   long save_stride;         // doubles per unit row = boards_pad * 8
+  int n_stages;             // weight ring depth (slots of kStageBytes)
+  long long *prof;          // optional [n_warps_total][8] phase cycle counters (CAB_FWD_PROFILE debug launches)
 };
 
-__global__ void __launch_bounds__(kThreads, 2) mlp_forward_kernel(const ForwardArgs args) {
+// shared memory carve-up, in this order
+__host__ __device__ inline size_t fwd_smem_ring(int n_stages) { return (size_t) n_stages * kStageBytes; }
+__host__ __device__ inline size_t fwd_smem_abuf(int n_pairs, int a_units) { return (size_t) n_pairs * a_units * kUnitBytes; }
+__host__ __device__ inline size_t fwd_smem_tail(int n_stages) {
+  return (size_t) kSmemChunks * sizeof(ChunkDesc) + (size_t) n_stages * (sizeof(uint64_t) + sizeof(uint32_t)) + 16;
+}
+
+#define CAB_PROF_T(var) long long var = 0; if (PROF) var = clock64();
+#define CAB_PROF_ACC(slot, t0) if (PROF) { prof_acc[slot] += clock64() - (t0); }
+
+template <bool PROF>
+__global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const ForwardArgs args) {
+  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CAB_PROF_T(t_kernel)
   extern __shared__ __align__(1024) uint8_t smem[];
+  const int n_stages = args.n_stages;
+  const int n_warps = (int) (blockDim.x >> 5), n_pairs = n_warps >> 1;
   uint8_t *ring = smem;
-  double2 *abuf_all = reinterpret_cast<double2 *>(smem + kStages * kStageBytes);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes +
-                                                (size_t) ((blockDim.x >> 5) - 1) * args.a_units * kUnitBytes);
-  uint64_t *empty = full + kStages;
+  double2 *abuf_all = reinterpret_cast<double2 *>(smem + fwd_smem_ring(n_stages));
+  ChunkDesc *s_chunks = reinterpret_cast<ChunkDesc *>(smem + fwd_smem_ring(n_stages) + fwd_smem_abuf(n_pairs, args.a_units));
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_chunks + kSmemChunks);
+  uint32_t *done = reinterpret_cast<uint32_t *>(full + n_stages);  // arrivals per ring slot, monotonically increasing
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_cons = (int) (blockDim.x >> 5) - 1;  // consumer warps in this launch (<= kConsumerWarps)
+  const int pair = warp >> 1, half = warp & 1;
+  // chunks this CTA will consume, in order: (groups it owns) x n_chunks
+  const long my_groups = args.n_groups > blockIdx.x ? (args.n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long total_chunks = my_groups * args.n_chunks;
+  const bool table_in_smem = args.n_chunks <= kSmemChunks;
+  const ChunkDesc *chunks = table_in_smem ? s_chunks : args.chunks;
+
+  if (table_in_smem) {
+    const int n16 = args.n_chunks * (int) (sizeof(ChunkDesc) / 16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x)
+      reinterpret_cast<int4 *>(s_chunks)[i] = reinterpret_cast<const int4 *>(args.chunks)[i];
+  }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], n_cons);
+      done[s] = 0;
     }
     mbar_fence_init();
+    for (int s = 0; s < n_stages && s < total_chunks; ++s) {  // initial fill of the ring
+      const ChunkDesc *d = &args.chunks[s % args.n_chunks];
+      mbar_arrive_expect_tx(&full[s], d->bytes);
+      bulk_g2s(ring + (size_t) s * kStageBytes, args.pack + d->src_off, d->bytes, &full[s]);
+    }
   }
   __syncthreads();
 
-  if (warp == n_cons) {
-    // ---------------- producer: stream the packed weights into the ring, once per board group ----------------
-    if (lane == 0) {
-      uint32_t cc = 0;
-      for (long g = blockIdx.x; g < args.n_groups; g += gridDim.x) {
-        for (int c = 0; c < args.n_chunks; ++c, ++cc) {
-          const uint32_t src_off = args.chunks[c].src_off, bytes = args.chunks[c].bytes;
-          const uint32_t s = cc % kStages, k = cc / kStages;
-          if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);
-          mbar_arrive_expect_tx(&full[s], bytes);
-          bulk_g2s(ring + (size_t) s * kStageBytes, args.pack + src_off, bytes, &full[s]);
-        }
-      }
-    }
-    return;
-  }
-
-  // ---------------- consumers ------------------------------------------------------------------------------
-  double2 *abuf = abuf_all + (size_t) warp * args.a_units * 32;
+  double2 *abuf = abuf_all + (size_t) pair * args.a_units * 32;
   const int m = lane >> 2, q = lane & 3;
-  double acc[kMaxNB][2];
-  uint32_t cc = 0;
+  double acc[kMaxNBH][2];
+  uint32_t rs = 0, rk = 0;   // ring slot of the current chunk, times the ring wrapped
+  long n = 0;                // sequence number of the current chunk within this CTA
+  const uint32_t abuf_addr = smem_u32(abuf) + (uint32_t) lane * 16u;
+  const uint32_t ring_addr = smem_u32(ring) + (uint32_t) lane * 16u;
 
   for (long g = blockIdx.x; g < args.n_groups; g += gridDim.x) {
-    const long board0 = (g * n_cons + warp) * kBoardsPerWarp;
+    const long board0 = (g * n_pairs + pair) * kBoardsPerWarp;
     const long board = board0 + m;
     const bool valid = board < args.n_boards;
+    double *save_lane = (args.save != nullptr && valid) ? args.save + board0 * 8 + lane * 2 : nullptr;
 
+    CAB_PROF_T(t_load)
     {
-      // Network::loadBoard (network.cpp:119-123): input = k * 0.4, bit-identical to Piece::code()
+      // Network::loadBoard (network.cpp:119-123): input = k * 0.4, bit-identical to Piece::code().
+      // The pair splits the 8 input units; the previous group's last reads of abuf ended at its final pair barrier.
       const int8_t *row = args.codes + (valid ? board : 0) * 64;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
+      for (int tt = 0; tt < 4; ++tt) {
+        const int t = 2 * tt + half;
         const int c0 = valid ? row[8 * t + 2 * q] : 0, c1 = valid ? row[8 * t + 2 * q + 1] : 0;
         const double2 x = make_double2((double) c0 * 0.4, (double) c1 * 0.4);
         abuf[t * 32 + lane] = x;
-        if (args.save != nullptr && valid)
-          *reinterpret_cast<double2 *>(args.save + (size_t) t * args.save_stride + board0 * 8 + lane * 2) = x;
+        if (save_lane != nullptr) *reinterpret_cast<double2 *>(save_lane + (size_t) t * args.save_stride) = x;
       }
+      pair_barrier(pair);
     }
+    CAB_PROF_ACC(0, t_load)
 
-    for (int c = 0; c < args.n_chunks; ++c, ++cc) {
-      const ChunkDesc d = args.chunks[c];
+    for (int c = 0; c < args.n_chunks; ++c, ++n) {
+      CAB_PROF_T(t_desc)
+      const ChunkDesc d = chunks[c];
       const bool first = d.flags & kFirst, last = d.flags & kLast;
+      const int nb0 = (d.nb + 1) >> 1;                     // tiles of half 0; half 1 takes the rest
+      const int j0 = half ? nb0 : 0, nbh = half ? d.nb - nb0 : nb0;
       if (first) {
 #pragma unroll
-        for (int j = 0; j < kMaxNB; ++j) acc[j][0] = acc[j][1] = 0.0;
+        for (int j = 0; j < kMaxNBH; ++j) acc[j][0] = acc[j][1] = 0.0;
       }
-      const uint32_t s = cc % kStages, k = cc / kStages;
-      mbar_wait(&full[s], k & 1);
-      const double2 *w = reinterpret_cast<const double2 *>(ring + (size_t) s * kStageBytes);
-      double2 *a_out = abuf + (size_t) d.a_out * 32;
-      dispatch_chunk(d.nb, acc, abuf + (size_t) (d.a_in + d.t0) * 32, w, d.tcount, lane, last, a_out);
+      CAB_PROF_ACC(1, t_desc)
+      CAB_PROF_T(t_wait)
+      mbar_wait(&full[rs], rk & 1);
+      CAB_PROF_ACC(2, t_wait)
+      CAB_PROF_T(t_mma)
+      dispatch_chunk(nbh, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
+                     ring_addr + rs * kStageBytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
+      CAB_PROF_ACC(3, t_mma)
 
+      CAB_PROF_T(t_refill)
+      // Release the slot. In-order issue means every load of this warp from the slot has returned before the
+      // atomic issues; the last warp to arrive therefore re-arms the slot with the chunk that is n_stages ahead.
+      if (lane == 0) {
+        const uint32_t old = atomicAdd(&done[rs], 1u);
+        if ((old + 1) % (uint32_t) n_warps == 0) {
+          const long refill = n + n_stages;
+          if (refill < total_chunks) {
+            const ChunkDesc *nd = &chunks[refill % args.n_chunks];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(&full[rs], nd->bytes);
+            bulk_g2s(ring + (size_t) rs * kStageBytes, args.pack + nd->src_off, nd->bytes, &full[rs]);
+          }
+        }
+      }
+      if (++rs == (uint32_t) n_stages) { rs = 0; ++rk; }
+      CAB_PROF_ACC(4, t_refill)
+
+      CAB_PROF_T(t_act)
       if (last) {
-        // a = f(theta) on this n-block, in place on the units this lane wrote itself (no cross-lane hazard)
-#pragma unroll 2
-        for (int j = 0; j < d.nb; ++j) {
+        // layer boundary: (1) both warps are done READING the layer input, (2) each writes a = f(theta) for its own
+        // tiles in place (a lane only ever touches the units it wrote itself), (3) outputs visible to the partner
+        double2 *a_out = abuf + (size_t) (d.a_out + j0) * 32;
+        pair_barrier(pair);
+        dispatch_store(nbh, acc, a_out, lane);
+        int j = 0;
+        for (; j + 4 <= nbh; j += 4) {   // 4 units = 8 independent activations in flight per lane
+          double2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = a_out[(j + u) * 32 + lane];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { v[u].x = act_f(v[u].x); v[u].y = act_f(v[u].y); }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            a_out[(j + u) * 32 + lane] = v[u];
+            if (save_lane != nullptr)
+              *reinterpret_cast<double2 *>(save_lane + (size_t) (d.save_off + d.tile0 + j0 + j + u) * args.save_stride) = v[u];
+          }
+        }
+        for (; j < nbh; ++j) {
           double2 v = a_out[j * 32 + lane];
           v.x = act_f(v.x);
           v.y = act_f(v.y);
           a_out[j * 32 + lane] = v;
-          if (args.save != nullptr && valid)
-            *reinterpret_cast<double2 *>(args.save + (size_t) (d.save_off + d.tile0 + j) * args.save_stride +
-                                         board0 * 8 + lane * 2) = v;
+          if (save_lane != nullptr)
+            *reinterpret_cast<double2 *>(save_lane + (size_t) (d.save_off + d.tile0 + j0 + j) * args.save_stride) = v;
         }
-        if ((d.flags & kFinal) && args.out != nullptr && valid && q == 0) args.out[board] = a_out[lane].x;
+        if ((d.flags & kFinal) && half == 0 && args.out != nullptr && valid && q == 0) args.out[board] = a_out[lane].x;
+        pair_barrier(pair);
       }
+      CAB_PROF_ACC(5, t_act)
     }
   }
+  if (PROF && args.prof != nullptr && lane == 0) {
+    prof_acc[6] = clock64() - t_kernel;
+    long long *dst = args.prof + ((long) blockIdx.x * n_warps + warp) * 8;
+    for (int i = 0; i < 8; ++i) dst[i] = prof_acc[i];
+  }
+  // every issued bulk copy has been waited on by every warp (total_chunks bounds the refills): nothing in flight at exit
 }
 
 }  // namespace cab
