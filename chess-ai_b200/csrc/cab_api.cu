@@ -176,7 +176,7 @@ static void build_plan(const cab_net *net, bool transposed, StreamPlan *plan) {
       sg.n_doubles = (long) t_in * nb * 64;
       plan->segs.push_back(sg);
       const int per_t_bytes = nb * kUnitBytes;
-      const int tpc = std::max(1, kStageBytes / per_t_bytes);
+      const int tpc = std::max(1, net->stage_bytes / per_t_bytes);
       for (int t0 = 0; t0 < t_in; t0 += tpc) {
         ChunkDesc d{};
         d.tcount = (uint16_t) std::min(tpc, t_in - t0);
@@ -221,8 +221,8 @@ static void free_plan(StreamPlan *plan) {
   plan->d_chunks = nullptr; plan->d_segs = nullptr; plan->d_pack = nullptr;
 }
 
-size_t forward_smem_bytes(int a_units, int n_cons, int n_stages) {
-  return fwd_smem_ring(n_stages) + fwd_smem_abuf(n_cons, a_units) + fwd_smem_tail(n_stages);
+size_t forward_smem_bytes(int a_units, int n_cons, int n_stages, int stage_bytes) {
+  return fwd_smem_ring(n_stages, stage_bytes) + fwd_smem_abuf(n_cons, a_units) + fwd_smem_tail(n_stages);
 }
 
 constexpr size_t kSmemMax = 227 * 1024;
@@ -230,7 +230,7 @@ constexpr size_t kSmemMax = 227 * 1024;
 // CTA geometry: warp PAIRS per CTA (8 boards each), weight-ring depth, CTAs per SM. Wide layers trade pairs for
 // activation space. n_cons counts pairs. CAB_FWD_PAIRS / CAB_FWD_STAGES override for experiments.
 struct Geometry { int n_cons, n_stages, ctas_per_sm; };
-Geometry choose_geometry(int a_units, long n_boards, int sm_count) {
+Geometry choose_geometry(int a_units, int stage_bytes, long n_boards, int sm_count) {
   static const int env_w = getenv("CAB_FWD_PAIRS") ? atoi(getenv("CAB_FWD_PAIRS")) : 0;
   static const int env_s = getenv("CAB_FWD_STAGES") ? atoi(getenv("CAB_FWD_STAGES")) : 0;
   (void) n_boards; (void) sm_count;
@@ -238,18 +238,20 @@ Geometry choose_geometry(int a_units, long n_boards, int sm_count) {
   const int max_pairs = kConsumerWarps / 2;
   const int want = env_w > 0 ? std::min(env_w, max_pairs) : max_pairs;
   for (int p = want; p >= 1; --p) {
-    if (forward_smem_bytes(a_units, p, 2) > kSmemMax) continue;
+    if (forward_smem_bytes(a_units, p, 2, stage_bytes) > kSmemMax) continue;
     g.n_cons = p;
-    int st = env_s > 0 ? std::min(env_s, kMaxStages) : 4;
-    while (st > 2 && forward_smem_bytes(a_units, p, st) > kSmemMax) --st;
+    static const int env_c = getenv("CAB_FWD_CTAS") ? atoi(getenv("CAB_FWD_CTAS")) : 0;
+    const size_t budget = (env_c == 2 && p <= max_pairs / 2) ? kSmemMax / 2 - 1024 : kSmemMax;
+    int st = env_s > 0 ? std::min(env_s, kMaxStages) : kMaxStages;
+    while (st > 2 && forward_smem_bytes(a_units, p, st, stage_bytes) > budget) --st;
     g.n_stages = st;
     // two CTAs per SM only when both fit and together keep <= 16 warps
-    g.ctas_per_sm = (p <= max_pairs / 2 && (forward_smem_bytes(a_units, p, st) + 1024) * 2 <= kSmemMax) ? 2 : 1;
+    g.ctas_per_sm = (p <= max_pairs / 2 && (forward_smem_bytes(a_units, p, st, stage_bytes) + 1024) * 2 <= kSmemMax) ? 2 : 1;
     return g;
   }
   return g;
 }
-int consumer_warps_for(int a_units) { return choose_geometry(a_units, 0, 148).n_cons; }
+int consumer_warps_for(int a_units, int stage_bytes) { return choose_geometry(a_units, stage_bytes, 0, 148).n_cons; }
 
 // (re)build the packed streams from d_w on `stream`
 int ensure_packed(cab_net *net, cudaStream_t stream) {
@@ -274,7 +276,8 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
   a.n_chunks = (int) net->fwd.chunks.size();
   a.a_units = net->fwd.a_units;
   a.n_boards = n_boards;
-  const Geometry geo = choose_geometry(a.a_units, n_boards, net->sm_count);
+  const Geometry geo = choose_geometry(a.a_units, net->stage_bytes, n_boards, net->sm_count);
+  a.stage_bytes = net->stage_bytes;
   const int n_cons = geo.n_cons;
   a.n_stages = geo.n_stages;
   const int boards_per_cta = n_cons * kBoardsPerWarp;
@@ -283,7 +286,7 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
   a.out = d_out;
   a.save = d_save;
   a.save_stride = save_stride;
-  const size_t smem = forward_smem_bytes(a.a_units, n_cons, geo.n_stages);
+  const size_t smem = forward_smem_bytes(a.a_units, n_cons, geo.n_stages, net->stage_bytes);
   const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * geo.ctas_per_sm);
   static const bool prof_env = getenv("CAB_FWD_PROFILE") != nullptr;
   if (prof_env) {
@@ -357,6 +360,7 @@ static int create_exact(const std::vector<int> &dims, int device, cab_net **out)
   CAB_CUDA(cudaGetDeviceProperties(&prop, device));
   net->sm_count = prop.multiProcessorCount;
   net->dims = dims;
+  net->stage_bytes = getenv("CAB_STAGE_KB") ? std::max(16, std::min(64, atoi(getenv("CAB_STAGE_KB")))) * 1024 : kStageBytes;
   long w = 0;
   uint32_t u = 0;
   for (size_t l = 0; l < dims.size(); ++l) {
@@ -372,7 +376,7 @@ static int create_exact(const std::vector<int> &dims, int device, cab_net **out)
   build_plan(net, true, &net->bwd);
   if ((rc = upload_plan(&net->fwd)) != CAB_OK) return rc;
   if ((rc = upload_plan(&net->bwd)) != CAB_OK) return rc;
-  if (consumer_warps_for(std::max(net->fwd.a_units, net->bwd.a_units)) == 0) {
+  if (consumer_warps_for(std::max(net->fwd.a_units, net->bwd.a_units), net->stage_bytes) == 0) {
     set_error("layer too wide for the fp64 stream kernel: %d activation units per warp do not fit shared memory",
               std::max(net->fwd.a_units, net->bwd.a_units));
     delete net;

@@ -25,7 +25,7 @@ constexpr int kConsumerWarps = 16;                      // max warps per CTA; a 
 constexpr int kMaxThreads = kConsumerWarps * 32;        // no producer warp: the last warp off a ring slot re-arms it
 constexpr int kBoardsPerWarp = 8;                       // boards per warp pair (one DMMA M tile)
 constexpr int kMaxStages = 8;                           // weight ring depth upper bound
-constexpr int kStageBytes = 32768;                      // one ring slot
+constexpr int kStageBytes = 49152;                      // default ring slot (measured best: 2 x 48 KB with 8 pairs)
 constexpr int kMaxNB = 32;                              // output tiles of one n-block (split over the pair)
 constexpr int kMaxNBH = 16;                             // output tiles one warp accumulates in registers
 constexpr int kUnitBytes = 512;                         // 32 lanes x double2
@@ -83,6 +83,7 @@ struct EvalCtx {  // per-caller scratch: lets many host threads evaluate on one 
 struct cab_net {
   int device = 0;
   int sm_count = 148;
+  int stage_bytes = cab::kStageBytes;  // ring slot size the stream plans were chunked for
   std::vector<int> dims;
   std::vector<long> woff;
   long n_weights = 0;
@@ -214,8 +215,9 @@ __device__ __forceinline__ double act_f(double x) {
 }
 // f'(x) = MAX * (1 - sig^2) / WIDTH with sig = modifiedSigmoid(x/WIDTH) = f(x)/MAX, so it is a function of a = f(x):
 __device__ __forceinline__ double act_df_from_a(double a) {
-  const double sig = a / 4.0;
-  return 4.0 * (1.0 - sig * sig) / 4.0;
+  const double sig = a / 4.0;                        // exact: a = 4 * sig
+  const double s2 = __dmul_rn(sig, sig);             // no FMA contraction: the x86 reference rounds sig*sig first
+  return __dmul_rn(4.0, __dadd_rn(1.0, -s2)) / 4.0;  // network.h:90
 }
 
 // Philox4x32-10 (Salmon et al. 2011); mirrors oracle/mlp_oracle.c:orc_philox4x32_10 bit for bit

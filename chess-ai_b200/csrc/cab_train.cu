@@ -1,7 +1,11 @@
 // cab_train.cu — training entry points of include/chessai_b200.h (Optimizer::optimize / dropout, train loop, DP).
+#include <dlfcn.h>
+
 #include <cstdio>
+#include <cstring>
 
 #include "cab_internal.cuh"
+#include "train_kernels.cuh"
 
 namespace cab {
 
@@ -25,6 +29,308 @@ __global__ void __launch_bounds__(256) dropout_kernel(double *__restrict__ w, lo
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(hits, local);
 }
 
+// declared in cab_api.cu
+int ensure_packed(cab_net *net, cudaStream_t stream);
+int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d_out, double *d_save, long save_stride,
+                   cudaStream_t stream);
+struct Geometry { int n_cons, n_stages, ctas_per_sm; };
+Geometry choose_geometry(int a_units, int stage_bytes, long n_boards, int sm_count);
+size_t forward_smem_bytes(int a_units, int n_cons, int n_stages, int stage_bytes);
+
+// ---- NCCL through dlopen: the library must load (and evaluate) on machines without NCCL -------------------------
+struct Id128 { char b[128]; };  // ncclUniqueId: 128 opaque bytes, passed BY VALUE to ncclCommInitRank
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.h != nullptr) return CAB_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) {
+    g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) { set_error("NCCL not found (dlopen libnccl.so.2): %s", dlerror()); return CAB_ENCCL; }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId)) dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank)) dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce)) dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy)) dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString)) dlsym(g_nccl.h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    set_error("NCCL library lacks required symbols");
+    return CAB_ENCCL;
+  }
+  return CAB_OK;
+}
+static int nccl_fail(int rc, const char *what) {
+  set_error("NCCL error %d in %s: %s", rc, what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return CAB_ENCCL;
+}
+constexpr int kNcclDouble = 8, kNcclSum = 0;  // ncclFloat64, ncclSum (nccl.h enums, stable across 2.x)
+
+// ---- training buffers ------------------------------------------------------------------------------------------
+static int ensure_train_state(cab_net *net) {
+  if (net->train_stream == nullptr) CAB_CUDA(cudaStreamCreateWithFlags(&net->train_stream, cudaStreamNonBlocking));
+  if (net->d_dw == nullptr) {
+    CAB_CUDA(cudaMalloc(&net->d_dw, net->n_weights * sizeof(double)));
+    CAB_CUDA(cudaMemset(net->d_dw, 0, net->n_weights * sizeof(double)));
+  }
+  if (net->d_grad == nullptr) {
+    CAB_CUDA(cudaMalloc(&net->d_grad, (net->n_weights + 4) * sizeof(double)));
+    CAB_CUDA(cudaMemset(net->d_grad, 0, (net->n_weights + 4) * sizeof(double)));
+  }
+  if (net->d_scalars == nullptr) {
+    CAB_CUDA(cudaMalloc(&net->d_scalars, 64 * sizeof(double)));
+    CAB_CUDA(cudaMemset(net->d_scalars, 0, 64 * sizeof(double)));
+  }
+  return CAB_OK;
+}
+
+static int ensure_batch_buffers(cab_net *net, long n) {
+  const long pad = (n + 63) / 64 * 64;
+  if (pad > net->train_cap) {
+    cudaFree(net->d_acts); cudaFree(net->d_psis); cudaFree(net->d_tout);
+    net->d_acts = net->d_psis = net->d_tout = nullptr;
+    const size_t bytes = (size_t) net->act_units_total * pad * 8 * sizeof(double);
+    CAB_CUDA(cudaMalloc(&net->d_acts, bytes));
+    CAB_CUDA(cudaMalloc(&net->d_psis, bytes));
+    CAB_CUDA(cudaMalloc(&net->d_tout, pad * sizeof(double)));
+    CAB_CUDA(cudaMemset(net->d_acts, 0, bytes));
+    CAB_CUDA(cudaMemset(net->d_psis, 0, bytes));
+    net->train_cap = pad;
+  }
+  return CAB_OK;
+}
+
+static int ensure_host_staging(cab_net *net, long n) {
+  if (n > net->tbuf_cap) {
+    cudaFree(net->d_tcodes); cudaFree(net->d_ttargets);
+    CAB_CUDA(cudaMalloc(&net->d_tcodes, n * 64));
+    CAB_CUDA(cudaMalloc(&net->d_ttargets, n * sizeof(double)));
+    net->tbuf_cap = n;
+  }
+  return CAB_OK;
+}
+
+// grad tasks (layer x tile blocks), built once per net and cached on the device
+struct GradPlan { GradTask *d_tasks = nullptr; int n_tasks = 0; };
+static std::mutex g_plan_mu;
+static std::vector<std::pair<cab_net *, GradPlan>> g_grad_plans;
+
+static int get_grad_plan(cab_net *net, GradPlan *out) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  for (auto &p : g_grad_plans)
+    if (p.first == net) { *out = p.second; return CAB_OK; }
+  std::vector<GradTask> tasks;
+  const int L = (int) net->dims.size();
+  for (int l = 0; l + 1 < L; ++l) {
+    const int K = net->dims[l], N = net->dims[l + 1];
+    const int kt = (K + 7) / 8, nt = (N + 7) / 8;
+    for (int k0 = 0; k0 < kt; k0 += kGK)
+      for (int n0 = 0; n0 < nt; n0 += kGN) {
+        GradTask t{};
+        t.a_unit = net->act_unit_off[l] + k0;
+        t.p_unit = net->act_unit_off[l + 1] + n0;
+        t.nkt = std::min(kGK, kt - k0);
+        t.nnt = std::min(kGN, nt - n0);
+        t.k0 = k0 * 8; t.n0 = n0 * 8;
+        t.K = K; t.N = N;
+        t.w_off = net->woff[l];
+        tasks.push_back(t);
+      }
+  }
+  GradPlan gp;
+  gp.n_tasks = (int) tasks.size();
+  CAB_CUDA(cudaMalloc(&gp.d_tasks, tasks.size() * sizeof(GradTask)));
+  CAB_CUDA(cudaMemcpy(gp.d_tasks, tasks.data(), tasks.size() * sizeof(GradTask), cudaMemcpyHostToDevice));
+  g_grad_plans.push_back({net, gp});
+  *out = gp;
+  return CAB_OK;
+}
+
+void drop_grad_plan(cab_net *net) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  for (size_t i = 0; i < g_grad_plans.size(); ++i)
+    if (g_grad_plans[i].first == net) {
+      cudaFree(g_grad_plans[i].second.d_tasks);
+      g_grad_plans.erase(g_grad_plans.begin() + i);
+      return;
+    }
+}
+
+static int launch_backward(cab_net *net, const double *d_targets, long n, cudaStream_t stream) {
+  BackwardArgs a{};
+  a.pack = reinterpret_cast<const uint8_t *>(net->bwd.d_pack);
+  a.chunks = net->bwd.d_chunks;
+  a.n_chunks = (int) net->bwd.chunks.size();
+  a.a_units = net->bwd.a_units;
+  a.n_boards = n;
+  const Geometry geo = choose_geometry(a.a_units, net->stage_bytes, n, net->sm_count);
+  a.n_stages = geo.n_stages;
+  a.stage_bytes = net->stage_bytes;
+  const int boards_per_cta = geo.n_cons * kBoardsPerWarp;
+  a.n_groups = (n + boards_per_cta - 1) / boards_per_cta;
+  a.targets = d_targets;
+  a.acts = net->d_acts;
+  a.psis = net->d_psis;
+  a.save_stride = net->train_cap * 8;
+  a.out_unit = net->act_unit_off.back();
+  a.err_sum = net->d_grad + net->n_weights;  // [sumE, sumE', count, spare]
+  const size_t smem = forward_smem_bytes(a.a_units, geo.n_cons, geo.n_stages, net->stage_bytes);
+  const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * geo.ctas_per_sm);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CAB_CUDA(cudaFuncSetAttribute(mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  mlp_backward_kernel<<<grid, geo.n_cons * 64, smem, stream>>>(a);
+  net->launches++;
+  CAB_CUDA(cudaGetLastError());
+  return CAB_OK;
+}
+
+static int launch_grad(cab_net *net, long n, cudaStream_t stream) {
+  GradPlan gp;
+  int rc = get_grad_plan(net, &gp);
+  if (rc != CAB_OK) return rc;
+  GradArgs a{};
+  a.tasks = gp.d_tasks;
+  a.n_tasks = gp.n_tasks;
+  a.n_boards_pad4 = (n + 3) / 4 * 4;
+  // enough (task, slice) warps to cover the chip a few times, slices of >= 64 boards
+  long slices = std::max<long>(1, (long) net->sm_count * 16 / std::max(1, gp.n_tasks));
+  long slice_boards = std::max<long>(64, (a.n_boards_pad4 + slices - 1) / slices);
+  slice_boards = (slice_boards + 3) / 4 * 4;
+  a.n_slices = (int) ((a.n_boards_pad4 + slice_boards - 1) / slice_boards);
+  a.slice_boards = slice_boards;
+  a.acts = net->d_acts;
+  a.psis = net->d_psis;
+  a.save_stride = net->train_cap * 8;
+  a.grad = net->d_grad;
+  const long warps = (long) a.n_tasks * a.n_slices;
+  grad_kernel<<<(int) ((warps + 3) / 4), 128, 0, stream>>>(a);
+  net->launches++;
+  CAB_CUDA(cudaGetLastError());
+  return CAB_OK;
+}
+
+static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d_targets, long n, double *lambda,
+                            double max_const, double rate, int *accepted, double *err, double *new_err,
+                            cudaStream_t stream) {
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  if ((rc = ensure_batch_buffers(net, n)) != CAB_OK) return rc;
+  const long nw = net->n_weights;
+  {
+    std::lock_guard<std::mutex> lk(net->mu);
+    if ((rc = ensure_packed(net, stream)) != CAB_OK) return rc;
+  }
+  CAB_CUDA(cudaMemsetAsync(net->d_grad, 0, (nw + 4) * sizeof(double), stream));
+  set_scalar_kernel<<<1, 1, 0, stream>>>(net->d_grad + nw + 2, (double) n);
+  // forward with saved activations (propagate_for_training), backward, gradient
+  if ((rc = launch_forward(net, d_codes, n, net->d_tout, net->d_acts, net->train_cap * 8, stream)) != CAB_OK) return rc;
+  if ((rc = launch_backward(net, d_targets, n, stream)) != CAB_OK) return rc;
+  if ((rc = launch_grad(net, n, stream)) != CAB_OK) return rc;
+  if (net->nccl_comm != nullptr) {  // sum of (G, E, -, count) over ranks
+    int nrc = g_nccl.AllReduce(net->d_grad, net->d_grad, (size_t) nw + 4, kNcclDouble, kNcclSum, net->nccl_comm, stream);
+    if (nrc != 0) return nccl_fail(nrc, "ncclAllReduce(grad)");
+  }
+  apply_update_kernel<<<(int) std::min<long>((nw + 255) / 256, 148L * 8), 256, 0, stream>>>(net->d_w, net->d_dw, net->d_grad, nw, *lambda);
+  net->launches += 2;
+  net->pack_dirty = true;
+  {
+    std::lock_guard<std::mutex> lk(net->mu);
+    if ((rc = ensure_packed(net, stream)) != CAB_OK) return rc;
+  }
+  // re-forward (network.cpp:265) and E'
+  if ((rc = launch_forward(net, d_codes, n, net->d_tout, nullptr, 0, stream)) != CAB_OK) return rc;
+  CAB_CUDA(cudaMemsetAsync(net->d_scalars, 0, 2 * sizeof(double), stream));
+  batch_error_kernel<<<(int) std::min<long>((n + 255) / 256, 148L * 4), 256, 0, stream>>>(net->d_tout, d_targets, n, net->d_scalars);
+  net->launches++;
+  if (net->nccl_comm != nullptr) {
+    int nrc = g_nccl.AllReduce(net->d_scalars, net->d_scalars, 1, kNcclDouble, kNcclSum, net->nccl_comm, stream);
+    if (nrc != 0) return nccl_fail(nrc, "ncclAllReduce(E')");
+  }
+  double h_first[3] = {0, 0, 0}, h_new = 0;
+  CAB_CUDA(cudaMemcpyAsync(h_first, net->d_grad + nw, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CAB_CUDA(cudaMemcpyAsync(&h_new, net->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CAB_CUDA(cudaStreamSynchronize(stream));
+  const double count = h_first[2];
+  const double e0 = h_first[0] / count, e1 = h_new / count;
+  const bool ok = e1 < e0;                                    // network.cpp:269
+  if (ok) {
+    if (*lambda < max_const) *lambda *= rate;                 // :270-271
+  } else {
+    *lambda /= rate;                                          // :273
+    rollback_kernel<<<(int) std::min<long>((nw + 255) / 256, 148L * 8), 256, 0, stream>>>(net->d_w, net->d_dw, nw);
+    net->launches++;
+    net->pack_dirty = true;
+    CAB_CUDA(cudaGetLastError());
+  }
+  if (accepted) *accepted = ok ? 1 : 0;
+  if (err) *err = e0;
+  if (new_err) *new_err = e1;
+  return CAB_OK;
+}
+
+static int train_sequence_impl(cab_net *net, const int8_t *codes, const double *targets, long n, double *lambda,
+                               double max_const, double rate, int reset_rule, uint64_t seed, uint8_t *accepted_host,
+                               int *resets, double *err, double *new_err) {
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  if ((rc = ensure_host_staging(net, n)) != CAB_OK) return rc;
+  cudaStream_t s = net->train_stream;
+  CAB_CUDA(cudaMemcpyAsync(net->d_tcodes, codes, n * 64, cudaMemcpyHostToDevice, s));
+  CAB_CUDA(cudaMemcpyAsync(net->d_ttargets, targets, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  uint8_t *d_acc = nullptr;
+  CAB_CUDA(cudaMalloc(&d_acc, n));
+  SeqArgs a{};
+  a.w = net->d_w; a.dw = net->d_dw;
+  a.codes = net->d_tcodes; a.targets = net->d_ttargets;
+  a.n_cases = n;
+  a.n_layers = (int) net->dims.size();
+  int off = 0;
+  for (int l = 0; l < a.n_layers; ++l) {
+    a.dims[l] = net->dims[l];
+    a.noff[l] = off;
+    off += net->dims[l];
+    if (l + 1 < a.n_layers) a.woff[l] = net->woff[l];
+  }
+  a.noff[a.n_layers] = off;
+  a.n_weights = net->n_weights;
+  a.lambda_io = net->d_scalars + 8;
+  a.max_const = max_const; a.rate = rate;
+  a.apply_reset_rule = reset_rule;
+  a.seed = seed;
+  a.accepted = d_acc;
+  a.resets = reinterpret_cast<int *>(net->d_scalars + 9);
+  a.err_out = net->d_scalars + 10;
+  CAB_CUDA(cudaMemcpyAsync(net->d_scalars + 8, lambda, sizeof(double), cudaMemcpyHostToDevice, s));
+  const size_t smem = (size_t) 4 * off * sizeof(double);
+  if (smem > 200 * 1024) { cudaFree(d_acc); set_error("network too wide for the sequential trainer"); return CAB_EINVAL; }
+  CAB_CUDA(cudaFuncSetAttribute(train_sequence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  train_sequence_kernel<<<1, 1024, smem, s>>>(a);
+  net->launches++;
+  CAB_CUDA(cudaGetLastError());
+  double h[4];
+  CAB_CUDA(cudaMemcpyAsync(h, net->d_scalars + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (accepted_host) CAB_CUDA(cudaMemcpyAsync(accepted_host, d_acc, n, cudaMemcpyDeviceToHost, s));
+  CAB_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_acc);
+  *lambda = h[0];
+  if (resets) memcpy(resets, &h[1], sizeof(int));
+  if (err) *err = h[2];
+  if (new_err) *new_err = h[3];
+  net->pack_dirty = true;
+  return CAB_OK;
+}
+
 }  // namespace cab
 
 using namespace cab;
@@ -34,6 +340,7 @@ extern "C" {
 int cab_dropout(cab_net *net, double rate, uint64_t seed, uint64_t offset, long *hits) {
   if (!net) { set_error("null argument"); return CAB_EINVAL; }
   CAB_CUDA(cudaSetDevice(net->device));
+  CAB_CUDA(cudaDeviceSynchronize());
   unsigned long long *d_hits = nullptr;
   CAB_CUDA(cudaMalloc(&d_hits, sizeof(unsigned long long)));
   CAB_CUDA(cudaMemset(d_hits, 0, sizeof(unsigned long long)));
@@ -49,27 +356,93 @@ int cab_dropout(cab_net *net, double rate, uint64_t seed, uint64_t offset, long 
   return CAB_OK;
 }
 
-int cab_train_case(cab_net *, const int8_t *, double, double *, double, double, int *, double *, double *) {
-  set_error("cab_train_case: not built yet");
-  return CAB_ESTATE;
+int cab_train_case(cab_net *net, const int8_t *codes64, double target, double *lambda, double max_const, double rate,
+                   int *accepted, double *err, double *new_err) {
+  if (!net || !codes64 || !lambda) { set_error("null argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  uint8_t acc = 0;
+  int rc = train_sequence_impl(net, codes64, &target, 1, lambda, max_const, rate, 0, 0, &acc, nullptr, err, new_err);
+  if (rc == CAB_OK && accepted) *accepted = acc;
+  return rc;
 }
-int cab_train_sequence(cab_net *, const int8_t *, const double *, long, double *, uint64_t, uint8_t *, int *) {
-  set_error("cab_train_sequence: not built yet");
-  return CAB_ESTATE;
+
+int cab_train_sequence(cab_net *net, const int8_t *codes, const double *targets, long n, double *lambda,
+                       uint64_t dropout_seed, uint8_t *accepted_host, int *resets) {
+  if (!net || !lambda || n < 0 || (n > 0 && (!codes || !targets))) { set_error("bad argument"); return CAB_EINVAL; }
+  if (resets) *resets = 0;
+  if (n == 0) return CAB_OK;
+  CAB_CUDA(cudaSetDevice(net->device));
+  return train_sequence_impl(net, codes, targets, n, lambda, 15.0, 1.1, 1, dropout_seed, accepted_host, resets, nullptr, nullptr);
 }
-int cab_train_batch_host(cab_net *, const int8_t *, const double *, long, double *, double, double, int *, double *,
-                         double *) {
-  set_error("cab_train_batch_host: not built yet");
-  return CAB_ESTATE;
+
+int cab_train_batch_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n, double *lambda,
+                        double max_const, double rate, int *accepted, double *err, double *new_err, void *stream) {
+  if (!net || !lambda || n <= 0 || !codes_dev || !targets_dev) { set_error("bad argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  return train_batch_impl(net, codes_dev, targets_dev, n, lambda, max_const, rate, accepted, err, new_err,
+                          stream ? (cudaStream_t) stream : net->train_stream);
 }
-int cab_train_batch_dev(cab_net *, const int8_t *, const double *, long, double *, double, double, int *, double *,
-                        double *, void *) {
-  set_error("cab_train_batch_dev: not built yet");
-  return CAB_ESTATE;
+
+int cab_train_batch_host(cab_net *net, const int8_t *codes, const double *targets, long n, double *lambda,
+                         double max_const, double rate, int *accepted, double *err, double *new_err) {
+  if (!net || !lambda || n <= 0 || !codes || !targets) { set_error("bad argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  if ((rc = ensure_host_staging(net, n)) != CAB_OK) return rc;
+  cudaStream_t s = net->train_stream;
+  CAB_CUDA(cudaMemcpyAsync(net->d_tcodes, codes, n * 64, cudaMemcpyHostToDevice, s));
+  CAB_CUDA(cudaMemcpyAsync(net->d_ttargets, targets, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  return train_batch_impl(net, net->d_tcodes, net->d_ttargets, n, lambda, max_const, rate, accepted, err, new_err, s);
 }
-int cab_dp_unique_id(void *) { set_error("cab_dp: not built yet"); return CAB_ESTATE; }
-int cab_dp_init(cab_net *, const void *, int, int) { set_error("cab_dp: not built yet"); return CAB_ESTATE; }
-int cab_dp_shutdown(cab_net *) { return CAB_OK; }
-int cab_grad_buffer(cab_net *, double **, long *) { set_error("cab_grad_buffer: not built yet"); return CAB_ESTATE; }
+
+int cab_dp_unique_id(void *id128_out) {
+  if (!id128_out) { set_error("null argument"); return CAB_EINVAL; }
+  int rc = load_nccl();
+  if (rc != CAB_OK) return rc;
+  int nrc = g_nccl.GetUniqueId(id128_out);
+  return nrc == 0 ? CAB_OK : nccl_fail(nrc, "ncclGetUniqueId");
+}
+
+int cab_dp_init(cab_net *net, const void *id128, int rank, int world) {
+  if (!net || !id128 || world < 1 || rank < 0 || rank >= world) { set_error("bad argument"); return CAB_EINVAL; }
+  int rc = load_nccl();
+  if (rc != CAB_OK) return rc;
+  CAB_CUDA(cudaSetDevice(net->device));
+  if ((rc = ensure_train_state(net)) != CAB_OK) return rc;
+  Id128 id;
+  memcpy(id.b, id128, 128);
+  void *comm = nullptr;
+  int nrc = g_nccl.CommInitRank(&comm, world, id, rank);
+  if (nrc != 0) return nccl_fail(nrc, "ncclCommInitRank");
+  net->nccl_comm = comm;
+  net->dp_rank = rank;
+  net->dp_world = world;
+  return CAB_OK;
+}
+
+int cab_dp_shutdown(cab_net *net) {
+  if (!net) return CAB_OK;
+  drop_grad_plan(net);
+  if (net->nccl_comm != nullptr && g_nccl.CommDestroy) {
+    g_nccl.CommDestroy(net->nccl_comm);
+    net->nccl_comm = nullptr;
+  }
+  net->dp_world = 1;
+  net->dp_rank = 0;
+  return CAB_OK;
+}
+
+int cab_grad_buffer(cab_net *net, double **grad_dev, long *n_doubles) {
+  if (!net || !grad_dev || !n_doubles) { set_error("null argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  *grad_dev = net->d_grad;
+  *n_doubles = net->n_weights + 4;
+  return CAB_OK;
+}
 
 }  // extern "C"

@@ -118,12 +118,13 @@ struct ForwardArgs {
   double *out;              // [n_boards] or nullptr
   double *save;             // saved activations in unit layout, or nullptr (K2: propagate_for_training)
   long save_stride;         // doubles per unit row = boards_pad * 8
-  int n_stages;             // weight ring depth (slots of kStageBytes)
+  int n_stages;             // weight ring depth
+  int stage_bytes;          // bytes per ring slot (the plan's chunk size limit)
   long long *prof;          // optional [n_warps_total][8] phase cycle counters (CAB_FWD_PROFILE debug launches)
 };
 
 // shared memory carve-up, in this order
-__host__ __device__ inline size_t fwd_smem_ring(int n_stages) { return (size_t) n_stages * kStageBytes; }
+__host__ __device__ inline size_t fwd_smem_ring(int n_stages, int stage_bytes) { return (size_t) n_stages * stage_bytes; }
 __host__ __device__ inline size_t fwd_smem_abuf(int n_pairs, int a_units) { return (size_t) n_pairs * a_units * kUnitBytes; }
 __host__ __device__ inline size_t fwd_smem_tail(int n_stages) {
   return (size_t) kSmemChunks * sizeof(ChunkDesc) + (size_t) n_stages * (sizeof(uint64_t) + sizeof(uint32_t)) + 16;
@@ -137,11 +138,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CAB_PROF_T(t_kernel)
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int n_stages = args.n_stages;
+  const int n_stages = args.n_stages, stage_bytes = args.stage_bytes;
   const int n_warps = (int) (blockDim.x >> 5), n_pairs = n_warps >> 1;
   uint8_t *ring = smem;
-  double2 *abuf_all = reinterpret_cast<double2 *>(smem + fwd_smem_ring(n_stages));
-  ChunkDesc *s_chunks = reinterpret_cast<ChunkDesc *>(smem + fwd_smem_ring(n_stages) + fwd_smem_abuf(n_pairs, args.a_units));
+  double2 *abuf_all = reinterpret_cast<double2 *>(smem + fwd_smem_ring(n_stages, stage_bytes));
+  ChunkDesc *s_chunks = reinterpret_cast<ChunkDesc *>(smem + fwd_smem_ring(n_stages, stage_bytes) + fwd_smem_abuf(n_pairs, args.a_units));
   uint64_t *full = reinterpret_cast<uint64_t *>(s_chunks + kSmemChunks);
   uint32_t *done = reinterpret_cast<uint32_t *>(full + n_stages);  // arrivals per ring slot, monotonically increasing
 
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
     for (int s = 0; s < n_stages && s < total_chunks; ++s) {  // initial fill of the ring
       const ChunkDesc *d = &args.chunks[s % args.n_chunks];
       mbar_arrive_expect_tx(&full[s], d->bytes);
-      bulk_g2s(ring + (size_t) s * kStageBytes, args.pack + d->src_off, d->bytes, &full[s]);
+      bulk_g2s(ring + (size_t) s * stage_bytes, args.pack + d->src_off, d->bytes, &full[s]);
     }
   }
   __syncthreads();
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
       CAB_PROF_ACC(2, t_wait)
       CAB_PROF_T(t_mma)
       dispatch_chunk(nbh, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
-                     ring_addr + rs * kStageBytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount);
+                     ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount);
       __syncwarp();
       CAB_PROF_ACC(3, t_mma)
 
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
             const ChunkDesc *nd = &chunks[refill % args.n_chunks];
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive_expect_tx(&full[rs], nd->bytes);
-            bulk_g2s(ring + (size_t) rs * kStageBytes, args.pack + nd->src_off, nd->bytes, &full[rs]);
+            bulk_g2s(ring + (size_t) rs * stage_bytes, args.pack + nd->src_off, nd->bytes, &full[rs]);
           }
         }
       }

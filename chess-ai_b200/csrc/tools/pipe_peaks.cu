@@ -136,6 +136,28 @@ __global__ void __launch_bounds__(kThreads) lds_kernel(double* out, long long* c
   if (s0 + s1 == 12345.678) out[threadIdx.x] = s0 + s1;
 }
 
+// accuracy of the MUFU.RCP64H seed (rcp.approx.ftz.f64) and of 1..3 Newton steps, over d in [1, 2^k)
+__global__ void rcp_probe_kernel(double* maxerr) {
+  double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (1 << 22); i += gridDim.x * blockDim.x) {
+    const double d = (1.0 + i * (1.0 / (1 << 22))) * (double) (1ull << (i % 40));
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    e0 = fmax(e0, fabs(fma(-d, y, 1.0)));
+    double r = fma(-d, y, 1.0); y = fma(y, r, y);
+    e1 = fmax(e1, fabs(fma(-d, y, 1.0)));
+    r = fma(-d, y, 1.0); y = fma(y, r, y);
+    e2 = fmax(e2, fabs(fma(-d, y, 1.0)));
+    r = fma(-d, y, 1.0); y = fma(y, r, y);
+    e3 = fmax(e3, fabs(fma(-d, y, 1.0)));
+  }
+  // max over the grid via atomicMax on the bit pattern (all values are non-negative)
+  atomicMax((unsigned long long*) &maxerr[0], (unsigned long long) __double_as_longlong(e0));
+  atomicMax((unsigned long long*) &maxerr[1], (unsigned long long) __double_as_longlong(e1));
+  atomicMax((unsigned long long*) &maxerr[2], (unsigned long long) __double_as_longlong(e2));
+  atomicMax((unsigned long long*) &maxerr[3], (unsigned long long) __double_as_longlong(e3));
+}
+
 template <typename F>
 static double best_ms(F launch, int reps = 10) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -208,7 +230,13 @@ int main() {
     printf("{\"bench\": \"dfma_latency\", \"ns_per_dependent_fma\": %.3f}\n", ms2 * 1e6 / (1 << 16));
   }
   // per-warp DMMA issue rate with few warps: 1 warp/SMSP, 8 independent tiles
-  for (int warps : {1, 4, 8, 16}) {
+  {
+    double* me; CK(cudaMallocManaged(&me, 4 * sizeof(double)));
+    for (int i = 0; i < 4; ++i) me[i] = 0;
+    rcp_probe_kernel<<<sms, 256>>>(me); CK(cudaDeviceSynchronize());
+    printf("{\"bench\": \"rcp_approx_f64\", \"max_abs_1_minus_dy\": {\"seed\": %.3e, \"nr1\": %.3e, \"nr2\": %.3e, \"nr3\": %.3e}}\n", me[0], me[1], me[2], me[3]);
+  }
+  for (int warps : {1, 4, 8}) {
     double ms = best_ms([&] { dmma_kernel<16, 0><<<sms, warps * 32>>>(out, iters, 1.0); });
     double fl = 2.0 * 256 * 16 * iters * (double)sms * warps;
     printf("{\"bench\": \"dmma884_warps\", \"warps_per_sm\": %d, \"ms\": %.4f, \"tflops\": %.3f}\n", warps, ms, fl / ms * 1e-9);

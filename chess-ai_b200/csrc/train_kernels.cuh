@@ -1,0 +1,384 @@
+// train_kernels.cuh — CUDA kernels of the training path (K2-K5).
+//
+// Reference: network::Optimizer::optimize / dropout (/root/reference/src/mcts_network/network.cpp:223-292) and the
+// train loop of /root/reference/src/main/network/train.cpp:39-68.
+//
+//  train_sequence_kernel   the reference step exactly as written, one case after another, in ONE persistent CTA:
+//                          same summation order (ascending i per output, ascending j per omega), separate multiply
+//                          and add (no FMA contraction), (psi*lambda)*a update, accept / reject with rollback, the
+//                          lambda reset + Philox dropout rule. This is the B == 1 parity path.
+//  mlp_backward_kernel     minibatch: psi/omega recurrences for 8 boards per warp pair on the fp64 tensor pipe, fed
+//                          by the packed W^T stream (same ring / pairing as the forward kernel); saves psi.
+//  grad_kernel             minibatch: G_l += A_l^T Psi_{l+1} (contraction over boards) on the fp64 tensor pipe.
+//  apply / rollback / error kernels: elementwise.
+#pragma once
+#include "cab_internal.cuh"
+#include "mlp_stream_kernel.cuh"
+
+namespace cab {
+
+// ---------------------------------------------------------------------------------------------------------------
+// B == 1, exact order
+// ---------------------------------------------------------------------------------------------------------------
+struct SeqArgs {
+  double *w, *dw;            // flat weights / last update, n,i,j order
+  const int8_t *codes;       // [n_cases][64]
+  const double *targets;     // [n_cases]
+  long n_cases;
+  int n_layers;
+  int dims[32];
+  long woff[32];
+  int noff[33];
+  long n_weights;
+  double *lambda_io;         // in: starting lambda, out: final lambda
+  double max_const, rate;
+  int apply_reset_rule;      // train.cpp:54-57 (lambda reset + dropout) after every step
+  unsigned long long seed;   // Philox key of the dropout
+  uint8_t *accepted;         // [n_cases] or nullptr
+  int *resets;               // out
+  double *err_out;           // [2]: E, E' of the LAST step
+};
+
+// forward over all layers on shared-memory neuron arrays; thread j owns output j (ascending-i sum, mul then add)
+__device__ __forceinline__ void seq_forward(const SeqArgs &a, double *neurons, double *thetas, bool store_thetas) {
+  for (int l = 1; l < a.n_layers; ++l) {
+    const int K = a.dims[l - 1], N = a.dims[l];
+    const double *W = a.w + a.woff[l - 1];
+    const double *in = neurons + a.noff[l - 1];
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      double sum = 0.0;
+#pragma unroll 4
+      for (int i = 0; i < K; ++i) sum = __dadd_rn(sum, __dmul_rn(in[i], W[(long) i * N + j]));  // network.cpp:108-109
+      if (store_thetas) thetas[a.noff[l] + j] = sum;                                             // :150
+      neurons[a.noff[l] + j] = act_f(sum);                                                       // :112 / :151
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1) train_sequence_kernel(const SeqArgs a) {
+  extern __shared__ double sm[];
+  const int nn = a.noff[a.n_layers];
+  double *neurons = sm, *thetas = sm + nn, *omegas = sm + 2 * nn, *psis = sm + 3 * nn;
+  __shared__ double s_lambda, s_err, s_new_err;
+  __shared__ int s_accept, s_resets;
+  const int out = a.n_layers - 1;
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) omegas[i] = 0.0;
+  if (threadIdx.x == 0) { s_lambda = *a.lambda_io; s_resets = 0; s_err = 0; s_new_err = 0; }
+  __syncthreads();
+
+  for (long c = 0; c < a.n_cases; ++c) {
+    // loadBoard (network.cpp:119-123 via :228)
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) neurons[i] = (double) a.codes[c * 64 + i] * 0.4;
+    __syncthreads();
+    seq_forward(a, neurons, thetas, true);                                                       // :229
+    const double target = a.targets[c];
+    if (threadIdx.x == 0) {
+      const double om = __dadd_rn(target, -neurons[a.noff[out]]);                                // :242
+      omegas[a.noff[out]] = om;
+      s_err = __dmul_rn(om, om) / 2.0;                                                           // :243
+    }
+    __syncthreads();
+    const double lambda = s_lambda;
+    for (int layer = out - 1; layer >= 0; --layer) {                                             // :248
+      const int nl = layer + 1, K = a.dims[layer], N = a.dims[nl];
+      double *W = a.w + a.woff[layer], *dW = a.dw + a.woff[layer];
+      // psi = omega * f'(theta); omega = 0  (:252-254). f'(theta) = 4*(1 - sig^2)/4 with sig = f(theta)/4 exactly.
+      for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        psis[a.noff[nl] + j] = __dmul_rn(omegas[a.noff[nl] + j], act_df_from_a(neurons[a.noff[nl] + j]));
+        omegas[a.noff[nl] + j] = 0.0;
+      }
+      __syncthreads();
+      // omega[i] += psi_j * W[i][j] for j ascending, with the PRE-update weights (:257)
+      const double *ps = psis + a.noff[nl];
+      for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        double om = omegas[a.noff[layer] + i];
+        const double *row = W + (long) i * N;
+#pragma unroll 4
+        for (int j = 0; j < N; ++j) om = __dadd_rn(om, __dmul_rn(ps[j], row[j]));
+        omegas[a.noff[layer] + i] = om;
+      }
+      __syncthreads();
+      // dW = (psi * lambda) * a ; W += dW  (:258-259)
+      const double *in = neurons + a.noff[layer];
+      const long total = (long) K * N;
+      for (long e = threadIdx.x; e < total; e += blockDim.x) {
+        const int i = (int) (e / N), j = (int) (e - (long) i * N);
+        const double d = __dmul_rn(__dmul_rn(ps[j], lambda), in[i]);
+        dW[e] = d;
+        W[e] = __dadd_rn(W[e], d);
+      }
+      __syncthreads();
+    }
+    seq_forward(a, neurons, thetas, false);                                                      // :265
+    if (threadIdx.x == 0) {
+      const double d = __dadd_rn(target, -neurons[a.noff[out]]);
+      s_new_err = __dmul_rn(d, d) / 2.0;                                                         // :266-267
+      s_accept = s_new_err < s_err;
+      if (s_accept) {
+        if (s_lambda < a.max_const) s_lambda = __dmul_rn(s_lambda, a.rate);                      // :269-271
+      } else {
+        s_lambda = s_lambda / a.rate;                                                            // :273
+      }
+      if (a.accepted != nullptr) a.accepted[c] = (uint8_t) s_accept;
+    }
+    __syncthreads();
+    if (!s_accept) {                                                                             // :274-277
+      for (long e = threadIdx.x; e < a.n_weights; e += blockDim.x) a.w[e] = __dadd_rn(a.w[e], -a.dw[e]);
+      __syncthreads();
+    }
+    if (a.apply_reset_rule) {                                                                    // train.cpp:54-57
+      const bool reset = s_lambda < 0.0001 || 10.0 < s_lambda;
+      __syncthreads();
+      if (reset) {
+        const unsigned long long offset = (unsigned long long) s_resets;
+        for (long e = threadIdx.x; e < a.n_weights; e += blockDim.x) {                           // network.cpp:281-292
+          uint32_t r[4];
+          philox4x32_10((uint32_t) e, (uint32_t) ((uint64_t) e >> 32), (uint32_t) offset, (uint32_t) (offset >> 32),
+                        (uint32_t) a.seed, (uint32_t) (a.seed >> 32), r);
+          if (u53(r[0], r[1]) < 0.01) a.w[e] = 2.0 * u53(r[2], r[3]) + -1.0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_lambda = 2.0; ++s_resets; }
+        __syncthreads();
+      }
+    }
+    __threadfence();
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *a.lambda_io = s_lambda;
+    if (a.resets != nullptr) *a.resets = s_resets;
+    if (a.err_out != nullptr) { a.err_out[0] = s_err; a.err_out[1] = s_new_err; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// minibatch: backward (psi / omega)
+// ---------------------------------------------------------------------------------------------------------------
+struct BackwardArgs {
+  const uint8_t *pack;       // packed fragment stream of W^T (layers L-2 .. 1)
+  const ChunkDesc *chunks;
+  int n_chunks;
+  int a_units;
+  long n_boards;
+  long n_groups;
+  const double *targets;     // [n_boards]
+  const double *acts;        // saved activations, unit layout
+  double *psis;              // out: psi of every non-input layer, same geometry as acts
+  long save_stride;
+  uint32_t out_unit;         // unit offset of the output layer inside acts / psis
+  int n_stages, stage_bytes;
+  double *err_sum;           // += sum_b (T - y)^2 / 2
+};
+
+__global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const BackwardArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int n_stages = args.n_stages, stage_bytes = args.stage_bytes;
+  const int n_warps = (int) (blockDim.x >> 5), n_pairs = n_warps >> 1;
+  uint8_t *ring = smem;
+  double2 *abuf_all = reinterpret_cast<double2 *>(smem + fwd_smem_ring(n_stages, stage_bytes));
+  ChunkDesc *s_chunks = reinterpret_cast<ChunkDesc *>(smem + fwd_smem_ring(n_stages, stage_bytes) + fwd_smem_abuf(n_pairs, args.a_units));
+  uint64_t *full = reinterpret_cast<uint64_t *>(s_chunks + kSmemChunks);
+  uint32_t *done = reinterpret_cast<uint32_t *>(full + n_stages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1, half = warp & 1;
+  const long my_groups = args.n_groups > blockIdx.x ? (args.n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long total_chunks = my_groups * args.n_chunks;
+  const bool table_in_smem = args.n_chunks <= kSmemChunks;
+  const ChunkDesc *chunks = table_in_smem ? s_chunks : args.chunks;
+  if (table_in_smem) {
+    const int n16 = args.n_chunks * (int) (sizeof(ChunkDesc) / 16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x)
+      reinterpret_cast<int4 *>(s_chunks)[i] = reinterpret_cast<const int4 *>(args.chunks)[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
+    mbar_fence_init();
+    for (int s = 0; s < n_stages && s < total_chunks; ++s) {
+      const ChunkDesc *d = &args.chunks[s % args.n_chunks];
+      mbar_arrive_expect_tx(&full[s], d->bytes);
+      bulk_g2s(ring + (size_t) s * stage_bytes, args.pack + d->src_off, d->bytes, &full[s]);
+    }
+  }
+  __syncthreads();
+
+  double2 *abuf = abuf_all + (size_t) pair * args.a_units * 32;
+  const int m = lane >> 2, q = lane & 3;
+  double acc[kMaxNBH][2];
+  uint32_t rs = 0, rk = 0;
+  long n = 0;
+  double err_local = 0.0;
+  const uint32_t abuf_addr = smem_u32(abuf) + (uint32_t) lane * 16u;
+  const uint32_t ring_addr = smem_u32(ring) + (uint32_t) lane * 16u;
+
+  for (long g = blockIdx.x; g < args.n_groups; g += gridDim.x) {
+    const long board0 = (g * n_pairs + pair) * kBoardsPerWarp;
+    const long board = board0 + m;
+    const bool valid = board < args.n_boards;
+    const size_t lane_off = (size_t) board0 * 8 + lane * 2;
+
+    // omega_out = T - y, E = omega^2/2 (network.cpp:242-243); psi_out = omega_out * f'(theta_out) (:252).
+    // The output layer is one feature wide: it lives in .x of the lanes with q == 0 of unit 0.
+    if (half == 0) {
+      double2 psi = make_double2(0.0, 0.0);
+      if (valid && q == 0) {
+        const double y = args.acts[(size_t) args.out_unit * args.save_stride + lane_off];
+        const double om = args.targets[board] - y;
+        err_local += om * om / 2.0;
+        psi.x = om * act_df_from_a(y);
+      }
+      abuf[lane] = psi;
+      *reinterpret_cast<double2 *>(args.psis + (size_t) args.out_unit * args.save_stride + lane_off) = psi;
+    }
+    pair_barrier(pair);
+
+    for (int c = 0; c < args.n_chunks; ++c, ++n) {
+      const ChunkDesc d = chunks[c];
+      const bool first = d.flags & kFirst, last = d.flags & kLast;
+      const int nb0 = (d.nb + 1) >> 1;
+      const int j0 = half ? nb0 : 0, nbh = half ? d.nb - nb0 : nb0;
+      if (first) {
+#pragma unroll
+        for (int j = 0; j < kMaxNBH; ++j) acc[j][0] = acc[j][1] = 0.0;
+      }
+      mbar_wait(&full[rs], rk & 1);
+      dispatch_chunk(nbh, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
+                     ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount);
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t old = atomicAdd(&done[rs], 1u);
+        if ((old + 1) % (uint32_t) n_warps == 0) {
+          const long refill = n + n_stages;
+          if (refill < total_chunks) {
+            const ChunkDesc *nd = &chunks[refill % args.n_chunks];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(&full[rs], nd->bytes);
+            bulk_g2s(ring + (size_t) rs * stage_bytes, args.pack + nd->src_off, nd->bytes, &full[rs]);
+          }
+        }
+      }
+      if (++rs == (uint32_t) n_stages) { rs = 0; ++rk; }
+
+      if (last) {
+        // the accumulators hold omega of layer d.layer (network.cpp:257); psi = omega * f'(theta) uses the saved
+        // activation a = f(theta) of that layer (:252). psi goes to the pair buffer (next contraction) and to global.
+        double2 *a_out = abuf + (size_t) (d.a_out + j0) * 32;
+        pair_barrier(pair);
+        dispatch_store(nbh, acc, a_out, lane);
+        for (int j = 0; j < nbh; ++j) {
+          const size_t goff = (size_t) (d.save_off + d.tile0 + j0 + j) * args.save_stride + lane_off;
+          double2 om = a_out[j * 32 + lane];
+          double2 av = make_double2(0.0, 0.0);
+          if (valid) av = *reinterpret_cast<const double2 *>(args.acts + goff);
+          om.x = valid ? om.x * act_df_from_a(av.x) : 0.0;
+          om.y = valid ? om.y * act_df_from_a(av.y) : 0.0;
+          a_out[j * 32 + lane] = om;
+          *reinterpret_cast<double2 *>(args.psis + goff) = om;
+        }
+        pair_barrier(pair);
+      }
+    }
+  }
+  if (args.err_sum != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) err_local += __shfl_xor_sync(0xffffffffu, err_local, o);
+    if (lane == 0 && err_local != 0.0) atomicAdd(args.err_sum, err_local);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// minibatch: weight gradient  G_l[k][n] += sum_b a_l[b][k] * psi_{l+1}[b][n]
+// One warp owns a block of up to kGK x kGN 8x8 tiles of one layer and a slice of the boards; per step of 4 boards it
+// loads kGK A fragments + kGN B fragments (256 contiguous bytes each: the unit layout is [unit][board][8]) and
+// issues kGK*kGN DMMAs (M = k features, N = n features, K = boards).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kGK = 4, kGN = 8;
+struct GradTask {
+  uint32_t a_unit, p_unit;   // first unit of the k-tiles inside acts, of the n-tiles inside psis
+  int nkt, nnt;              // tiles in this block (<= kGK, <= kGN)
+  int k0, n0;                // first feature indices
+  int K, N;                  // layer shape
+  long w_off;
+};
+struct GradArgs {
+  const GradTask *tasks;
+  int n_tasks;
+  int n_slices;
+  long slice_boards;         // multiple of 4
+  long n_boards_pad4;        // boards rounded up to 4
+  const double *acts, *psis;
+  long save_stride;
+  double *grad;
+};
+
+__global__ void __launch_bounds__(128) grad_kernel(const GradArgs args) {
+  const int warp_global = (int) ((blockIdx.x * (long) blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= args.n_tasks * args.n_slices) return;
+  const GradTask t = args.tasks[warp_global / args.n_slices];
+  const int slice = warp_global % args.n_slices;
+  const long b_lo = slice * args.slice_boards, b_hi = min(b_lo + args.slice_boards, args.n_boards_pad4);
+  double acc[kGK][kGN][2];
+#pragma unroll
+  for (int i = 0; i < kGK; ++i)
+#pragma unroll
+    for (int j = 0; j < kGN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  // lane (r = lane>>2, c = lane&3): A[k = 8kt + r][board b + c], B[board b + c][n = 8nt + r]
+  const size_t lane_off = (size_t) (lane & 3) * 8 + (lane >> 2);
+  for (long b = b_lo; b < b_hi; b += 4) {
+    double af[kGK], bf[kGN];
+#pragma unroll
+    for (int i = 0; i < kGK; ++i)
+      af[i] = i < t.nkt ? __ldg(args.acts + (size_t) (t.a_unit + i) * args.save_stride + (size_t) b * 8 + lane_off) : 0.0;
+#pragma unroll
+    for (int j = 0; j < kGN; ++j)
+      bf[j] = j < t.nnt ? __ldg(args.psis + (size_t) (t.p_unit + j) * args.save_stride + (size_t) b * 8 + lane_off) : 0.0;
+#pragma unroll
+    for (int i = 0; i < kGK; ++i)
+#pragma unroll
+      for (int j = 0; j < kGN; ++j)
+        if (i < t.nkt && j < t.nnt) dmma884(acc[i][j], af[i], bf[j]);
+  }
+  // C[row = lane>>2][col = 2*(lane&3) + {0,1}] -> G[k][n]
+#pragma unroll
+  for (int i = 0; i < kGK; ++i)
+#pragma unroll
+    for (int j = 0; j < kGN; ++j) {
+      if (i >= t.nkt || j >= t.nnt) continue;
+      const int k = t.k0 + 8 * i + (lane >> 2), nn = t.n0 + 8 * j + 2 * (lane & 3);
+      if (k < t.K) {
+        if (nn < t.N) atomicAdd(args.grad + t.w_off + (long) k * t.N + nn, acc[i][j][0]);
+        if (nn + 1 < t.N) atomicAdd(args.grad + t.w_off + (long) k * t.N + nn + 1, acc[i][j][1]);
+      }
+    }
+}
+
+// dW = (lambda / count) * G ; W += dW     (batch mean of network.cpp:258-259). count = grad[n + 2].
+__global__ void __launch_bounds__(256) apply_update_kernel(double *__restrict__ w, double *__restrict__ dw,
+                                                            const double *__restrict__ grad, long n, double lambda) {
+  const double scale = lambda / grad[n + 2];
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+    const double d = grad[i] * scale;
+    dw[i] = d;
+    w[i] += d;
+  }
+}
+// W -= dW   (network.cpp:274-277)
+__global__ void __launch_bounds__(256) rollback_kernel(double *__restrict__ w, const double *__restrict__ dw, long n) {
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) w[i] -= dw[i];
+}
+// sum_b (T - y)^2 / 2 over a batch of network outputs
+__global__ void __launch_bounds__(256) batch_error_kernel(const double *__restrict__ y, const double *__restrict__ t, long n,
+                                                           double *__restrict__ err_sum) {
+  double e = 0.0;
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+    const double d = t[i] - y[i];
+    e += d * d / 2.0;
+  }
+  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+  if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(err_sum, e);
+}
+__global__ void set_scalar_kernel(double *p, double v) { *p = v; }
+
+}  // namespace cab

@@ -1,0 +1,152 @@
+"""GPU parity of the training path (K2-K5) through the C ABI against the pinned oracle and the reference's golden traces.
+
+  * cab_train_case / cab_train_sequence restate Optimizer::optimize in the reference's own operation order, so the
+    accept / reject decisions and therefore lambda must match EXACTLY; weights agree to ~1e-12 (exp / reciprocal
+    rounding only).
+  * cab_train_batch_* is the minibatch extension; its checker is oracle/mlp_oracle.c:orc_train_batch.
+Tolerances are written next to each assertion.
+"""
+import numpy as np
+import pytest
+
+from conftest import DEFAULT_DIMS, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def latest(cab, golden):
+    return cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"])
+
+
+def test_optimize_board20_rejected_like_reference(cab, latest, golden):
+    g = golden["json"]["optimize_board20"]
+    lam, acc, e0, e1 = cab.Optimizer.optimize(latest, golden["case_codes"][20], float(golden["case_targets"][20]), 2.0)
+    assert acc is False
+    assert lam == g["lambda_after"]                      # 2.0 / 1.1, exact
+    assert e1 >= e0
+    y = latest.predict_batch(golden["case_codes"][20:21])[0]
+    assert abs(y - g["prediction_after"]) < 1e-12        # W + dW - dW is not bit-reversible; both sides do it
+
+
+def test_epoch_over_the_66_cases_matches_reference(cab, latest, golden):
+    g = golden["json"]["epoch_latest"]
+    lam, acc, resets = cab.Optimizer.train_sequence(latest, golden["case_codes"], golden["case_targets"], 2.0)
+    assert lam == g["final_lambda"]                      # every decision identical -> identical lambda
+    assert resets == g["resets"] == 0
+    assert acc.sum() == 0
+    w = latest.get_weights()
+    assert np.abs(w[::257] - golden["epoch_weights_sample"]).max() < 1e-10
+    assert abs(latest.predict_batch(golden["case_codes"][20:21])[0] - g["predict_board20"]) < 1e-10
+
+
+def test_trace_with_accepts_matches_reference_until_first_reset(cab, port, golden):
+    # reference: Network::randomNetwork() in a fresh process, 400 optimize steps cycling over the 66 cases
+    mt = port.mt_new()
+    w0 = port.random_net(DEFAULT_DIMS, mt).get_weights()
+    assert np.array_equal(w0[::101], golden["random_default_weights_sample"])
+    ref_l = golden["trace_lambdas"]
+    net = cab.Network.from_weights(DEFAULT_DIMS, w0)
+    codes, targets = golden["case_codes"], golden["case_targets"]
+    lam, lams = 2.0, []
+    for s in range(400):
+        lam, acc, e0, e1 = cab.Optimizer.optimize(net, codes[s % 66], float(targets[s % 66]), lam)
+        lams.append(lam)
+        if lam < 1e-4 or lam > 10.0:   # the reference resets here and draws dropout from mt19937: streams diverge
+            break
+    n = len(lams)
+    assert n > 20 and np.any(np.diff(lams) > 0) and np.any(np.diff(lams) < 0)   # the trace has accepts and rejects
+    assert ref_l[n - 1] == 2.0                      # the reference reset lambda at exactly this step
+    assert np.array_equal(np.array(lams[:n - 1]), ref_l[:n - 1])   # identical decisions up to there
+
+
+def test_sequence_with_resets_matches_port_oracle_bitwise_decisions(cab, port, golden):
+    # same loop, dropout = Philox(seed, reset index) on both sides -> decisions, lambda and resets identical
+    mt = port.mt_new()
+    pn = port.random_net(DEFAULT_DIMS, mt)
+    net = cab.Network.from_weights(DEFAULT_DIMS, pn.get_weights())
+    idx = np.arange(400) % 66
+    codes, targets = golden["case_codes"][idx], golden["case_targets"][idx]
+    resets_p, lam_p, acc_p = pn.train_sequence(codes, targets, 2.0, philox_seed=0xABCDEF)
+    lam_g, acc_g, resets_g = cab.Optimizer.train_sequence(net, codes, targets, 2.0, dropout_seed=0xABCDEF)
+    assert resets_p >= 1
+    assert resets_g == resets_p
+    assert np.array_equal(acc_g, acc_p)
+    assert lam_g == lam_p
+    # 400 chained steps amplify the 1-ulp exp/reciprocal differences; weights are O(1), so an absolute bound
+    assert np.abs(net.get_weights() - pn.get_weights()).max() < 1e-9
+
+
+def test_minibatch_of_one_equals_optimize(cab, port, golden):
+    pn = port.net_from_weights(DEFAULT_DIMS, golden["latest_weights"])
+    net = cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"])
+    c, t = golden["case_codes"][7:8], golden["case_targets"][7:8]
+    acc_p, lam_p, e0_p, e1_p = pn.optimize(c[0], float(t[0]), 0.05)
+    lam_g, acc_g, e0_g, e1_g = cab.Optimizer.train_batch(net, c, t, 0.05)
+    assert (acc_g, lam_g) == (bool(acc_p), lam_p)
+    assert abs(e0_g - e0_p) <= 1e-9 * abs(e0_p) and abs(e1_g - e1_p) <= 1e-9 * abs(e1_p)
+    assert np.abs(net.get_weights() - pn.get_weights()).max() < 1e-9
+
+
+@pytest.mark.parametrize("n,lam", [(66, 0.5), (256, 0.01), (1000, 2.0), (37, 1e-3)])
+def test_minibatch_step_vs_port_oracle(cab, port, golden, n, lam):
+    rng = np.random.default_rng(n)
+    w = rng.uniform(-0.3, 0.3, 64216)
+    pn = port.net_from_weights(DEFAULT_DIMS, w)
+    net = cab.Network.from_weights(DEFAULT_DIMS, w)
+    codes = golden["syn_codes"][:n]
+    targets = rng.uniform(-2, 2, n)
+    acc_p, lam_p, e0_p, e1_p = pn.train_batch(codes, targets, lam)
+    lam_g, acc_g, e0_g, e1_g = cab.Optimizer.train_batch(net, codes, targets, lam)
+    assert abs(e0_g - e0_p) <= 1e-10 * abs(e0_p)
+    assert abs(e1_g - e1_p) <= 1e-8 * abs(e1_p)
+    assert (acc_g, lam_g) == (bool(acc_p), lam_p)
+    assert np.abs(net.get_weights() - pn.get_weights()).max() < 1e-10
+
+
+def test_minibatch_descends_on_a_learnable_target(cab, golden):
+    # teacher = latest.txt outputs; a random student must reduce the batch error over accepted steps
+    teacher = cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"])
+    codes = golden["syn_codes"]
+    targets = teacher.predict_batch(codes)
+    student = cab.Network.randomNetwork(DEFAULT_DIMS, seed=7)
+    student.set_weights(student.get_weights() * 0.05)
+    lam, first, last, accepts = 0.5, None, None, 0
+    for step in range(30):
+        lam, acc, e0, e1 = cab.Optimizer.train_batch(student, codes, targets, lam)
+        first = e0 if first is None else first
+        if acc:
+            accepts += 1
+            last = e1
+        if lam < 1e-4 or lam > 10:
+            lam = 2.0
+    assert accepts >= 5 and last < first
+
+
+def test_dropout_philox_bitwise_and_rate(cab, port, golden):
+    pn = port.net_from_weights(DEFAULT_DIMS, golden["latest_weights"])
+    net = cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"])
+    hits_p = pn.dropout_philox(0.01, 0x5EED, 3)
+    hits_g = cab.Optimizer.dropout(net, 0.01, seed=0x5EED, offset=3)
+    assert hits_g == hits_p
+    w = net.get_weights()
+    assert np.array_equal(w, pn.get_weights())
+    changed = w != golden["latest_weights"]
+    assert changed.sum() == hits_g
+    assert 450 < hits_g < 850                      # Binomial(64216, 0.01): mean 642, sd 25
+    assert np.all(np.abs(w[changed]) < 1.0)        # replacements are U(-1, 1)
+    assert abs(w[changed].mean()) < 0.1
+    # a different offset touches a different set
+    net2 = cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"])
+    cab.Optimizer.dropout(net2, 0.01, seed=0x5EED, offset=4)
+    assert not np.array_equal(net2.get_weights() != golden["latest_weights"], changed)
+
+
+def test_random_network_is_philox_uniform(cab, port):
+    net = cab.Network.randomNetwork(DEFAULT_DIMS, seed=1234, stream=9)
+    w = net.get_weights()
+    assert w.min() >= -1.0 and w.max() < 1.0 and abs(w.mean()) < 0.02 and abs(w.std() - 3 ** -0.5) < 0.01
+    for i in (0, 1, 777, 64215):
+        r = port.philox([i, 0, 9, 0], [1234, 0])
+        u = ((int(r[3]) << 32 | int(r[2])) >> 11) / 2.0 ** 53
+        assert w[i] == 2.0 * u - 1.0
