@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=int(os.environ.get("CAB_BENCH_STREAMS", "4")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-throughput section")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -257,6 +258,56 @@ def main():
         e2e_s = float(t.item())
     e2e_value = world * N_BOARDS * e2e_steps / e2e_s
 
+    # ---- training throughput (second half of BASELINE.json's metric; configs[3] shape, reported beside the headline) ---
+    # data-parallel minibatch steps of Optimizer::optimize's extension: B_TRAIN synthetic boards per GPU per step,
+    # teacher targets = latest.txt outputs + N(0, 0.05), NCCL all-reduce of the gradient inside the library.
+    train = None
+    if not args.no_train:
+        dpm = importlib.import_module("chess-ai_b200.dp")
+        B_TRAIN = 65536
+        tcodes = dev_sets[1][:B_TRAIN]
+        ttargets = torch.empty(B_TRAIN, dtype=torch.float64, device="cuda")
+        net.eval_dev_ptr(tcodes.data_ptr(), B_TRAIN, ttargets.data_ptr(), main_stream.cuda_stream)
+        torch.cuda.synchronize()
+        gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        ttargets = (ttargets + 0.05 * torch.randn(B_TRAIN, dtype=torch.float64, device="cuda", generator=gen)).clamp_(-4, 4)
+        student = cab.Network.randomNetwork(DEFAULT_DIMS, device=local_rank, seed=1234)   # same seed: identical replicas
+        student.set_weights(student.get_weights() * 0.1)
+        par = dpm.DataParallel(cab, student) if world > 1 else None
+        lam, accepts, t_steps = 0.5, 0, 8
+
+        def train_step(lam):
+            if par is not None:
+                return par.train_batch_dev(tcodes.data_ptr(), ttargets.data_ptr(), B_TRAIN, lam)
+            import ctypes as C
+            lam_c, acc, e0, e1 = C.c_double(lam), C.c_int(0), C.c_double(0), C.c_double(0)
+            cab._ck(cab.lib().cab_train_batch_dev(student._h, tcodes.data_ptr(), ttargets.data_ptr(), B_TRAIN, C.byref(lam_c),
+                                                  15.0, 1.1, C.byref(acc), C.byref(e0), C.byref(e1), None))
+            return lam_c.value, bool(acc.value), e0.value, e1.value
+
+        for _ in range(2):
+            lam, acc, e_first, _ = train_step(lam)
+        l0 = student.launch_count
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(t_steps):
+            lam, acc, e0, e1 = train_step(lam)
+            accepts += int(acc)
+            if lam < 1e-4 or lam > 10.0:
+                lam = 2.0
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        train = {"value": world * B_TRAIN * t_steps / dt, "unit": "samples/s", "batch_per_gpu": B_TRAIN, "steps": t_steps,
+                 "ms_per_step": dt / t_steps * 1e3, "accepted_steps": accepts, "E_first": e_first, "E_last": e1 if acc else e0,
+                 "flop_per_sample": 577944, "gpu_launches": int(student.launch_count - l0),
+                 "collective": "ncclAllReduce(64220 fp64) + 1 scalar per step" if world > 1 else "none"}
+        if par is not None:
+            par.shutdown()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -291,6 +342,17 @@ def main():
         cpu_baseline = {"value": rate, "unit": "evals/s", "cores": used, "kind": kind,
                         "sample": "%d of the same synthetic boards x 4 passes, one Network::clone() per thread" % CPU_SAMPLE_BOARDS,
                         "max_rel_diff_vs_gpu": agree}
+        try:  # Optimizer::optimize is inherently sequential per network: 1 thread
+            from oracle_bind import RefOracle
+            if RefOracle.available():
+                rnet = RefOracle().net_from_weights(DEFAULT_DIMS, latest_weights())
+                n_t = 4096
+                secs, _ = rnet.time_train(codes[:n_t], np.zeros(n_t), 2.0)
+                cpu_baseline["train_value"] = n_t / secs
+                cpu_baseline["train_unit"] = "samples/s"
+                cpu_baseline["train_sample"] = "%d Optimizer::optimize steps, 1 thread" % n_t
+        except Exception as exc:  # the eval baseline stands on its own
+            cpu_baseline["train_error"] = str(exc)
 
     line = {
         "metric": "MLP board evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
@@ -299,7 +361,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": N_BOARDS * 64, "d2h_bytes_per_step": N_BOARDS * 8,
                 "steps": e2e_steps, "api": "cab_eval_host (pinned host buffers)"},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": sampler.summary(),
-        "parity_max_rel_err_vs_reference_golden": parity, "streams": len(streams),
+        "parity_max_rel_err_vs_reference_golden": parity, "streams": len(streams), "train": train,
     }
     print(json.dumps(line))
     if world > 1:
