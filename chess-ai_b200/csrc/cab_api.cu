@@ -195,7 +195,7 @@ static void build_plan(const cab_net *net, bool transposed, StreamPlan *plan) {
         d.n_tiles = (uint16_t) n_tiles;
         d.save_off = transposed ? net->act_unit_off[l] : net->act_unit_off[l + 1];
         d.save_in = transposed ? net->act_unit_off[l + 1] : net->act_unit_off[l];
-        if (!transposed && l > 0 && b == 0) d.flags |= kActIn;  // first n-block activates (and writes back) its input
+        if (!transposed && l > 0) d.flags |= kActIn;  // the layer input holds pre-activations when the JIT kernel runs
         plan->chunks.push_back(d);
       }
       off += sg.n_doubles;
@@ -226,6 +226,7 @@ size_t forward_smem_bytes(int a_units, int n_cons, int n_stages, int stage_bytes
 }
 
 constexpr size_t kSmemMax = 227 * 1024;
+constexpr bool kDefaultJit = false;  // activation applied just-in-time on the A-operand load (see mlp_stream_kernel.cuh)
 
 // CTA geometry: warp PAIRS per CTA (8 boards each), weight-ring depth, CTAs per SM. Wide layers trade pairs for
 // activation space. n_cons counts pairs. CAB_FWD_PAIRS / CAB_FWD_STAGES override for experiments.
@@ -289,6 +290,7 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
   const size_t smem = forward_smem_bytes(a.a_units, n_cons, geo.n_stages, net->stage_bytes);
   const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * geo.ctas_per_sm);
   static const bool prof_env = getenv("CAB_FWD_PROFILE") != nullptr;
+  static const bool jit = getenv("CAB_FWD_JIT") ? atoi(getenv("CAB_FWD_JIT")) != 0 : kDefaultJit;
   if (prof_env) {
     // debug: per-warp phase cycle counters of ONE launch, printed to stderr (never on by default)
     long long *d_prof = nullptr;
@@ -296,8 +298,10 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
     CAB_CUDA(cudaMalloc(&d_prof, nw * 8 * sizeof(long long)));
     CAB_CUDA(cudaMemset(d_prof, 0, nw * 8 * sizeof(long long)));
     a.prof = d_prof;
-    CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    mlp_forward_kernel<true><<<grid, n_cons * 64, smem, stream>>>(a);
+    CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (jit) mlp_forward_kernel<true, true><<<grid, n_cons * 64, smem, stream>>>(a);
+    else mlp_forward_kernel<true, false><<<grid, n_cons * 64, smem, stream>>>(a);
     CAB_CUDA(cudaStreamSynchronize(stream));
     std::vector<long long> h(nw * 8);
     CAB_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -305,12 +309,13 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
     double sum[8] = {0};
     for (long w = 0; w < nw; ++w) for (int i = 0; i < 8; ++i) sum[i] += (double) h[w * 8 + i];
     fprintf(stderr, "[cab profile] boards=%ld grid=%d pairs/cta=%d stages=%d  avg cycles per warp: load=%.0f desc=%.0f wait_full=%.0f "
-            "mma=%.0f refill=%.0f act=%.0f total=%.0f\n", n_boards, grid, n_cons, geo.n_stages, sum[0] / nw, sum[1] / nw, sum[2] / nw,
-            sum[3] / nw, sum[4] / nw, sum[5] / nw, sum[6] / nw);
+            "mma=%.0f refill=%.0f act(incl pair barriers)=%.0f pair_barriers=%.0f total=%.0f\n", n_boards, grid, n_cons, geo.n_stages, sum[0] / nw, sum[1] / nw, sum[2] / nw,
+            sum[3] / nw, sum[4] / nw, sum[5] / nw, sum[7] / nw, sum[6] / nw);
     net->launches++;
     return CAB_OK;
   }
-  mlp_forward_kernel<false><<<grid, n_cons * 64, smem, stream>>>(a);
+  if (jit) mlp_forward_kernel<false, true><<<grid, n_cons * 64, smem, stream>>>(a);
+  else mlp_forward_kernel<false, false><<<grid, n_cons * 64, smem, stream>>>(a);
   net->launches++;
   CAB_CUDA(cudaGetLastError());
   return CAB_OK;
@@ -382,7 +387,8 @@ static int create_exact(const std::vector<int> &dims, int device, cab_net **out)
     delete net;
     return CAB_EINVAL;
   }
-  CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   net->pack_dirty = true;
   *out = net;
   return CAB_OK;

@@ -34,15 +34,30 @@ __device__ __forceinline__ void pair_barrier(int pair) {  // named barrier 1 + p
   asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
 }
 
+// A-operand load of one input unit. ACT (just-in-time activation): the unit still holds the previous layer's
+// pre-activations theta; f() is applied here, one input unit ahead of its use, so the exp / reciprocal chain overlaps
+// the DMMA issue of the current unit instead of forming a phase of its own. Both warps of a pair do this redundantly
+// (each needs every input unit); nothing is written back.
+template <bool ACT>
+__device__ __forceinline__ double2 load_a(uint32_t addr, const double *tbl, double *save_row) {
+  double2 a = lds_frag(addr);
+  if (ACT) {
+    a.x = act_f_tbl(a.x, tbl);
+    a.y = act_f_tbl(a.y, tbl);
+    if (save_row != nullptr) *reinterpret_cast<double2 *>(save_row) = a;
+  }
+  return a;
+}
+
 // One chunk = tcount input units x NBH output tiles of this warp's half. B fragments are fetched one group of kG
 // tiles ahead (across the t boundary too); inside a group the kG ".x" DMMAs are issued before the dependent ".y" ones.
 constexpr int kG = 2;
-template <int NBH>
+template <int NBH, bool ACT>
 __device__ __forceinline__ void run_chunk(double (&acc)[kMaxNBH][2], uint32_t a_addr, uint32_t w_addr, uint32_t t_stride,
-                                          int tcount) {
+                                          int tcount, const double *tbl, double *save_row, long save_stride) {
   constexpr int NG = (NBH + kG - 1) / kG;
   double2 bcur[kG], bnxt[kG];
-  double2 a = lds_frag(a_addr);
+  double2 a = load_a<ACT>(a_addr, tbl, save_row);
 #pragma unroll
   for (int i = 0; i < kG; ++i)
     if (i < NBH) bcur[i] = lds_frag(w_addr + i * kUnitBytes);
@@ -50,7 +65,9 @@ __device__ __forceinline__ void run_chunk(double (&acc)[kMaxNBH][2], uint32_t a_
     const uint32_t wt = w_addr + (uint32_t) t * t_stride;
     const bool more = t + 1 < tcount;
     double2 a_next = a;
-    if (more) a_next = lds_frag(a_addr + (uint32_t) (t + 1) * kUnitBytes);
+    if (more)
+      a_next = load_a<ACT>(a_addr + (uint32_t) (t + 1) * kUnitBytes, tbl,
+                           save_row != nullptr ? save_row + (size_t) (t + 1) * save_stride : nullptr);
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       if (g + 1 < NG) {
@@ -81,10 +98,14 @@ __device__ __forceinline__ void store_acc(const double (&acc)[kMaxNBH][2], doubl
   for (int j = 0; j < NBH; ++j) a_out[j * 32 + lane] = make_double2(acc[j][0], acc[j][1]);
 }
 
-#define CAB_NB_CASE(N) \
-  case N: run_chunk<N>(acc, a_addr, w_addr, t_stride, tcount); break;
-__device__ __forceinline__ void dispatch_chunk(int nbh, double (&acc)[kMaxNBH][2], uint32_t a_addr, uint32_t w_addr,
-                                               uint32_t t_stride, int tcount) {
+#define CAB_NB_CASE(N)                                                                                     \
+  case N:                                                                                                  \
+    if (act_in) run_chunk<N, true>(acc, a_addr, w_addr, t_stride, tcount, tbl, save_row, save_stride);     \
+    else run_chunk<N, false>(acc, a_addr, w_addr, t_stride, tcount, nullptr, nullptr, 0);                  \
+    break;
+__device__ __forceinline__ void dispatch_chunk(int nbh, bool act_in, double (&acc)[kMaxNBH][2], uint32_t a_addr,
+                                               uint32_t w_addr, uint32_t t_stride, int tcount, const double *tbl,
+                                               double *save_row, long save_stride) {
   switch (nbh) {
     CAB_NB_CASE(1) CAB_NB_CASE(2) CAB_NB_CASE(3) CAB_NB_CASE(4) CAB_NB_CASE(5) CAB_NB_CASE(6) CAB_NB_CASE(7)
     CAB_NB_CASE(8) CAB_NB_CASE(9) CAB_NB_CASE(10) CAB_NB_CASE(11) CAB_NB_CASE(12) CAB_NB_CASE(13) CAB_NB_CASE(14)
@@ -127,13 +148,14 @@ struct ForwardArgs {
 __host__ __device__ inline size_t fwd_smem_ring(int n_stages, int stage_bytes) { return (size_t) n_stages * stage_bytes; }
 __host__ __device__ inline size_t fwd_smem_abuf(int n_pairs, int a_units) { return (size_t) n_pairs * a_units * kUnitBytes; }
 __host__ __device__ inline size_t fwd_smem_tail(int n_stages) {
-  return (size_t) kSmemChunks * sizeof(ChunkDesc) + (size_t) n_stages * (sizeof(uint64_t) + sizeof(uint32_t)) + 16;
+  return (size_t) kSmemChunks * sizeof(ChunkDesc) + 32 * sizeof(double) + (size_t) n_stages * (sizeof(uint64_t) + sizeof(uint32_t)) + 16;
 }
 
 #define CAB_PROF_T(var) long long var = 0; if (PROF) var = clock64();
 #define CAB_PROF_ACC(slot, t0) if (PROF) { prof_acc[slot] += clock64() - (t0); }
 
-template <bool PROF>
+// JIT = false: f() in an epilogue on each warp's own output tiles (a phase).  JIT = true: f() on the A-operand load.
+template <bool PROF, bool JIT>
 __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const ForwardArgs args) {
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CAB_PROF_T(t_kernel)
@@ -143,7 +165,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
   uint8_t *ring = smem;
   double2 *abuf_all = reinterpret_cast<double2 *>(smem + fwd_smem_ring(n_stages, stage_bytes));
   ChunkDesc *s_chunks = reinterpret_cast<ChunkDesc *>(smem + fwd_smem_ring(n_stages, stage_bytes) + fwd_smem_abuf(n_pairs, args.a_units));
-  uint64_t *full = reinterpret_cast<uint64_t *>(s_chunks + kSmemChunks);
+  double *exp_tbl = reinterpret_cast<double *>(s_chunks + kSmemChunks);  // 2^(j/32) for the table-driven exp
+  uint64_t *full = reinterpret_cast<uint64_t *>(exp_tbl + 32);
   uint32_t *done = reinterpret_cast<uint32_t *>(full + n_stages);  // arrivals per ring slot, monotonically increasing
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,6 +182,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
     for (int i = threadIdx.x; i < n16; i += blockDim.x)
       reinterpret_cast<int4 *>(s_chunks)[i] = reinterpret_cast<const int4 *>(args.chunks)[i];
   }
+  if (threadIdx.x >= 32 && threadIdx.x < 64) exp_tbl[threadIdx.x - 32] = c_exp2_tbl[threadIdx.x - 32];
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], 1);
@@ -219,8 +243,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
       mbar_wait(&full[rs], rk & 1);
       CAB_PROF_ACC(2, t_wait)
       CAB_PROF_T(t_mma)
-      dispatch_chunk(nbh, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
-                     ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount);
+      double *save_row = (JIT && half == 0 && save_lane != nullptr) ? save_lane + (size_t) (d.save_in + d.t0) * args.save_stride : nullptr;
+      dispatch_chunk(nbh, JIT && (d.flags & kActIn), acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
+                     ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount,
+                     exp_tbl, save_row, args.save_stride);
       __syncwarp();
       CAB_PROF_ACC(3, t_mma)
 
@@ -247,15 +273,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
         // layer boundary: (1) both warps are done READING the layer input, (2) each writes a = f(theta) for its own
         // tiles in place (a lane only ever touches the units it wrote itself), (3) outputs visible to the partner
         double2 *a_out = abuf + (size_t) (d.a_out + j0) * 32;
+        CAB_PROF_T(t_bar1)
         pair_barrier(pair);
+        CAB_PROF_ACC(7, t_bar1)
         dispatch_store(nbh, acc, a_out, lane);
-        int j = 0;
+        int j = JIT ? nbh : 0;   // JIT: the raw pre-activations stay in the buffer; the consumer applies f()
+        if (JIT && (d.flags & kFinal) && half == 0) {
+          double2 v = a_out[lane];
+          v.x = act_f_tbl(v.x, exp_tbl);
+          v.y = act_f_tbl(v.y, exp_tbl);
+          a_out[lane] = v;
+          if (save_lane != nullptr) *reinterpret_cast<double2 *>(save_lane + (size_t) d.save_off * args.save_stride) = v;
+        }
         for (; j + 4 <= nbh; j += 4) {   // 4 units = 8 independent activations in flight per lane
           double2 v[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) v[u] = a_out[(j + u) * 32 + lane];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) { v[u].x = act_f(v[u].x); v[u].y = act_f(v[u].y); }
+          for (int u = 0; u < 4; ++u) { v[u].x = act_f_tbl(v[u].x, exp_tbl); v[u].y = act_f_tbl(v[u].y, exp_tbl); }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             a_out[(j + u) * 32 + lane] = v[u];
@@ -265,14 +300,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
         }
         for (; j < nbh; ++j) {
           double2 v = a_out[j * 32 + lane];
-          v.x = act_f(v.x);
-          v.y = act_f(v.y);
+          v.x = act_f_tbl(v.x, exp_tbl);
+          v.y = act_f_tbl(v.y, exp_tbl);
           a_out[j * 32 + lane] = v;
           if (save_lane != nullptr)
             *reinterpret_cast<double2 *>(save_lane + (size_t) (d.save_off + d.tile0 + j0 + j) * args.save_stride) = v;
         }
         if ((d.flags & kFinal) && half == 0 && args.out != nullptr && valid && q == 0) args.out[board] = a_out[lane].x;
+        CAB_PROF_T(t_bar2)
         pair_barrier(pair);
+        CAB_PROF_ACC(7, t_bar2)
       }
       CAB_PROF_ACC(5, t_act)
     }

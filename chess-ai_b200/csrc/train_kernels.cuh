@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
   uint8_t *ring = smem;
   double2 *abuf_all = reinterpret_cast<double2 *>(smem + fwd_smem_ring(n_stages, stage_bytes));
   ChunkDesc *s_chunks = reinterpret_cast<ChunkDesc *>(smem + fwd_smem_ring(n_stages, stage_bytes) + fwd_smem_abuf(n_pairs, args.a_units));
-  uint64_t *full = reinterpret_cast<uint64_t *>(s_chunks + kSmemChunks);
+  // same carve-up as the forward kernel (the 32 doubles after the chunk table are its exp table; unused here)
+  uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(s_chunks + kSmemChunks) + 32);
   uint32_t *done = reinterpret_cast<uint32_t *>(full + n_stages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -244,8 +245,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
         for (int j = 0; j < kMaxNBH; ++j) acc[j][0] = acc[j][1] = 0.0;
       }
       mbar_wait(&full[rs], rk & 1);
-      dispatch_chunk(nbh, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
-                     ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount);
+      dispatch_chunk(nbh, false, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
+                     ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount,
+                     nullptr, nullptr, 0);
       __syncwarp();
       if (lane == 0) {
         const uint32_t old = atomicAdd(&done[rs], 1u);
