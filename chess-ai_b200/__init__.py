@@ -61,6 +61,8 @@ _SIGS = {
     "cab_eval_host": [_vp, _vp, C.c_long, _vp],
     "cab_eval_dev": [_vp, _vp, C.c_long, _vp, _vp],
     "cab_eval_dev_batches": [_vp, _vp, C.c_long, C.c_long, _vp, C.POINTER(_vp), C.c_int],
+    "cab_eval_bf16_dev": [_vp, _vp, C.c_long, _vp, _vp],
+    "cab_eval_bf16_host": [_vp, _i8p, C.c_long, _f64p],
     "cab_eval_records_host": [_vp, _u8p, C.c_long, _f64p],
     "cab_forward_full_host": [_vp, _i8p, C.c_long, _f64p],
     "cab_train_case": [_vp, _i8p, C.c_double, _dp, C.c_double, C.c_double, _ip, _dp, _dp],
@@ -311,6 +313,16 @@ class Network:
         """ceil(n/batch) asynchronous launches of `batch` boards, round-robin over the given cudaStream_t handles."""
         arr = (_vp * len(streams))(*streams)
         _ck(lib().cab_eval_dev_batches(self._h, codes_dev_ptr, n, batch, out_dev_ptr, arr, len(streams)))
+
+    def predict_batch_bf16(self, codes):
+        """bf16 tcgen05 forward (wide networks only: hidden widths multiples of 256)."""
+        c = _as_codes(codes)
+        out = np.zeros(len(c), dtype=np.float64)
+        _ck(lib().cab_eval_bf16_host(self._h, c.reshape(-1), len(c), out))
+        return out
+
+    def eval_bf16_dev_ptr(self, codes_dev_ptr, n, out_dev_ptr, stream=0):
+        _ck(lib().cab_eval_bf16_dev(self._h, codes_dev_ptr, n, out_dev_ptr, stream))
 
     def forward_full(self, codes):
         """Network::propagate_for_training (network.cpp:139-153): activations of every layer, [B, sum(dims[1:])]."""

@@ -225,6 +225,8 @@ size_t forward_smem_bytes(int a_units, int n_cons, int n_stages, int stage_bytes
   return fwd_smem_ring(n_stages, stage_bytes) + fwd_smem_abuf(n_cons, a_units) + fwd_smem_tail(n_stages);
 }
 
+void tc_free(cab_net *net);  // cab_tc.cu
+
 constexpr size_t kSmemMax = 227 * 1024;
 constexpr bool kDefaultJit = false;  // activation applied just-in-time on the A-operand load (see mlp_stream_kernel.cuh)
 
@@ -271,6 +273,11 @@ int ensure_packed(cab_net *net, cudaStream_t stream) {
 int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d_out, double *d_save, long save_stride,
                    cudaStream_t stream) {
   if (n_boards <= 0) return CAB_OK;
+  if (!net->fp64_ok) {
+    set_error("layer too wide for the fp64 stream kernel (%d activation units per pair exceed shared memory); "
+              "use the bf16 tcgen05 path (cab_eval_bf16_*)", net->fwd.a_units);
+    return CAB_EINVAL;
+  }
   ForwardArgs a{};
   a.pack = reinterpret_cast<const uint8_t *>(net->fwd.d_pack);
   a.chunks = net->fwd.d_chunks;
@@ -381,15 +388,12 @@ static int create_exact(const std::vector<int> &dims, int device, cab_net **out)
   build_plan(net, true, &net->bwd);
   if ((rc = upload_plan(&net->fwd)) != CAB_OK) return rc;
   if ((rc = upload_plan(&net->bwd)) != CAB_OK) return rc;
-  if (consumer_warps_for(std::max(net->fwd.a_units, net->bwd.a_units), net->stage_bytes) == 0) {
-    set_error("layer too wide for the fp64 stream kernel: %d activation units per warp do not fit shared memory",
-              std::max(net->fwd.a_units, net->bwd.a_units));
-    delete net;
-    return CAB_EINVAL;
-  }
+  // very wide layers do not fit the fp64 stream kernel's per-pair activation buffer: the network is still usable
+  // through the bf16 tcgen05 path (cab_eval_bf16_*); the fp64 entry points then return CAB_EINVAL
+  net->fp64_ok = consumer_warps_for(std::max(net->fwd.a_units, net->bwd.a_units), net->stage_bytes) > 0;
   CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  net->pack_dirty = true;
+  net->pack_dirty = net->tc_dirty = true;
   *out = net;
   return CAB_OK;
 }
@@ -491,6 +495,7 @@ int cab_net_destroy(cab_net *net) {
   if (!net) return CAB_OK;
   cudaSetDevice(net->device);
   cab_dp_shutdown(net);
+  tc_free(net);
   for (EvalCtx *c : net->ctxs) {
     for (int i = 0; i < 2; ++i) {
       if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
@@ -543,7 +548,7 @@ int cab_net_set_weights(cab_net *net, const double *w, long n) {
   if (rc != CAB_OK) return rc;
   CAB_CUDA(cudaDeviceSynchronize());
   CAB_CUDA(cudaMemcpy(net->d_w, w, n * sizeof(double), cudaMemcpyHostToDevice));
-  net->pack_dirty = true;
+  net->pack_dirty = net->tc_dirty = true;
   return CAB_OK;
 }
 
@@ -565,7 +570,7 @@ int cab_net_randomize(cab_net *net, uint64_t seed, uint64_t stream) {
   net->launches++;
   CAB_CUDA(cudaGetLastError());
   CAB_CUDA(cudaDeviceSynchronize());
-  net->pack_dirty = true;
+  net->pack_dirty = net->tc_dirty = true;
   return CAB_OK;
 }
 
@@ -575,7 +580,7 @@ int cab_net_zero(cab_net *net) {
   if (rc != CAB_OK) return rc;
   CAB_CUDA(cudaDeviceSynchronize());
   CAB_CUDA(cudaMemset(net->d_w, 0, net->n_weights * sizeof(double)));
-  net->pack_dirty = true;
+  net->pack_dirty = net->tc_dirty = true;
   return CAB_OK;
 }
 

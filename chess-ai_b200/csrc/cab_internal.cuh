@@ -89,6 +89,9 @@ struct cab_net {
   long n_weights = 0;
   double *d_w = nullptr;     // flat weights
   bool pack_dirty = true;    // packed streams stale w.r.t. d_w
+  bool fp64_ok = true;       // the fp64 stream kernels fit this network's widest layer in shared memory
+  bool tc_dirty = true;      // bf16 copies of the tcgen05 path stale w.r.t. d_w
+  void *tc = nullptr;        // cab::TcState of the bf16 tcgen05 path (cab_tc.cu), created on first use
   cab::StreamPlan fwd, bwd;
   // saved-activation geometry (units per board-group, per layer)
   std::vector<uint32_t> act_unit_off;  // per layer l (0..L-1): first unit of layer l's activations

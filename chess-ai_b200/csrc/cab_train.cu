@@ -223,6 +223,7 @@ static int launch_grad(cab_net *net, long n, cudaStream_t stream) {
 static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d_targets, long n, double *lambda,
                             double max_const, double rate, int *accepted, double *err, double *new_err,
                             cudaStream_t stream) {
+  if (!net->fp64_ok) { set_error("layer too wide for the fp64 training kernels"); return CAB_EINVAL; }
   int rc = ensure_train_state(net);
   if (rc != CAB_OK) return rc;
   if ((rc = ensure_batch_buffers(net, n)) != CAB_OK) return rc;
@@ -243,7 +244,7 @@ static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d
   }
   apply_update_kernel<<<(int) std::min<long>((nw + 255) / 256, 148L * 8), 256, 0, stream>>>(net->d_w, net->d_dw, net->d_grad, nw, *lambda);
   net->launches += 2;
-  net->pack_dirty = true;
+  net->pack_dirty = net->tc_dirty = true;
   {
     std::lock_guard<std::mutex> lk(net->mu);
     if ((rc = ensure_packed(net, stream)) != CAB_OK) return rc;
@@ -270,7 +271,7 @@ static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d
     *lambda /= rate;                                          // :273
     rollback_kernel<<<(int) std::min<long>((nw + 255) / 256, 148L * 8), 256, 0, stream>>>(net->d_w, net->d_dw, nw);
     net->launches++;
-    net->pack_dirty = true;
+    net->pack_dirty = net->tc_dirty = true;
     CAB_CUDA(cudaGetLastError());
   }
   if (accepted) *accepted = ok ? 1 : 0;
@@ -327,7 +328,7 @@ static int train_sequence_impl(cab_net *net, const int8_t *codes, const double *
   if (resets) memcpy(resets, &h[1], sizeof(int));
   if (err) *err = h[2];
   if (new_err) *new_err = h[3];
-  net->pack_dirty = true;
+  net->pack_dirty = net->tc_dirty = true;
   return CAB_OK;
 }
 
@@ -352,7 +353,7 @@ int cab_dropout(cab_net *net, double rate, uint64_t seed, uint64_t offset, long 
   CAB_CUDA(cudaMemcpy(&h, d_hits, sizeof h, cudaMemcpyDeviceToHost));
   cudaFree(d_hits);
   if (hits) *hits = (long) h;
-  net->pack_dirty = true;
+  net->pack_dirty = net->tc_dirty = true;
   return CAB_OK;
 }
 

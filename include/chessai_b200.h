@@ -94,6 +94,14 @@ CAB_API int cab_eval_records_host(cab_net *net, const uint8_t *records_host, lon
  * acts_host receives n_boards * sum(dims[1..]) doubles, board-major, layers concatenated in order. */
 CAB_API int cab_forward_full_host(cab_net *net, const int8_t *codes_host, long n_boards, double *acts_host);
 
+/* ---- bf16 tensor-core forward (tcgen05 + TMEM + TMA) for WIDE networks ------------------------------------------ */
+/* Same forward (network.cpp:92-117) with bf16 operands, fp32 accumulation in tensor memory and f() in fp32. Only for
+ * networks whose hidden widths are multiples of 256 (e.g. Network({2048,2048,2048,2048})); CAB_EINVAL otherwise.
+ * Stated tolerance vs the fp64 path: |dy| <= 0.15 on the (-4, 4) output scale for weights U(-1,1)/sqrt(fan_in),
+ * identical sign of the evaluation away from |y| < 0.15 (tests/test_tc_gpu.py). */
+CAB_API int cab_eval_bf16_dev(cab_net *net, const int8_t *codes_dev, long n_boards, double *out_dev, void *stream);
+CAB_API int cab_eval_bf16_host(cab_net *net, const int8_t *codes_host, long n_boards, double *out_host);
+
 /* ---- training (network::Optimizer  network.cpp:223-292, train loop main/network/train.cpp:39-68) ---------------- */
 /* Optimizer::optimize on ONE case: forward, backprop with in-place update (step lambda), re-forward, accept
  * (lambda *= rate while lambda < max_const) or reject (lambda /= rate and roll the update back). */

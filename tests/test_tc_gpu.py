@@ -1,0 +1,70 @@
+"""GPU parity of the bf16 tcgen05 path (K8, BASELINE.json configs[4]) against the fp64 oracle.
+
+Stated tolerance (bf16 operands, fp32 accumulation, hardware tanh): |dy| <= 0.15 on the (-4, 4) output scale for
+weights U(-1,1)/sqrt(fan_in); the sign of the evaluation (what move ranking uses) must agree wherever |y| >= 0.15.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ATOL = 0.15
+
+
+def scaled_weights(dims, seed, gain=2.0):
+    rng = np.random.default_rng(seed)
+    parts = []
+    for k, n in zip(dims[:-1], dims[1:]):
+        parts.append((rng.uniform(-1, 1, (k, n)) * gain / np.sqrt(k)).reshape(-1))
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("dims,n", [([64, 256, 256, 1], 300), ([64, 512, 256, 1], 1000), ([64, 2048, 2048, 2048, 2048, 1], 200)])
+def test_bf16_forward_vs_fp64_oracle(cab, port, golden, dims, n):
+    w = scaled_weights(dims, sum(dims))
+    net = cab.Network.from_weights(dims, w)
+    codes = np.ascontiguousarray(np.tile(golden["syn_codes"], (2, 1))[:n])
+    y = net.predict_batch_bf16(codes)
+    want = port.net_from_weights(dims, w).predict(codes[:min(n, 200)])
+    assert np.all(np.isfinite(y))
+    err = np.abs(y[:len(want)] - want)
+    assert err.max() < ATOL, err.max()
+    strong = np.abs(want) >= ATOL
+    assert strong.sum() > len(want) // 4
+    assert np.array_equal(np.sign(y[:len(want)][strong]), np.sign(want[strong]))
+
+
+def test_bf16_matches_gpu_fp64_on_a_net_both_paths_support(cab, golden):
+    dims = [64, 256, 256, 1]
+    w = scaled_weights(dims, 3)
+    net = cab.Network.from_weights(dims, w)
+    codes = golden["syn_codes"][:2048]
+    y64 = net.predict_batch(codes)
+    y16 = net.predict_batch_bf16(codes)
+    assert np.abs(y16 - y64).max() < ATOL
+    # ragged batch sizes (tile tails) and repeated calls
+    for n in (1, 127, 128, 129, 257):
+        assert np.abs(net.predict_batch_bf16(codes[:n]) - y64[:n]).max() < ATOL
+
+
+def test_bf16_tracks_weight_updates(cab, golden):
+    dims = [64, 256, 1]
+    net = cab.Network.from_weights(dims, scaled_weights(dims, 5))
+    codes = golden["syn_codes"][:256]
+    a = net.predict_batch_bf16(codes)
+    net.set_weights(scaled_weights(dims, 6))
+    b = net.predict_batch_bf16(codes)
+    assert np.abs(b - net.predict_batch(codes)).max() < ATOL and np.abs(a - b).max() > 0.2
+
+
+def test_default_net_is_refused_by_the_bf16_path(cab, golden):
+    net = cab.Network.from_weights([64, 144, 225, 100, 1], golden["latest_weights"])
+    with pytest.raises(cab.CabError) as e:
+        net.predict_batch_bf16(golden["syn_codes"][:8])
+    assert e.value.code == cab.CAB_EINVAL
+
+
+def test_wide_net_is_refused_by_the_fp64_stream_kernel(cab, golden):
+    net = cab.Network([64, 2048, 2048, 1])
+    with pytest.raises(cab.CabError) as e:
+        net.predict_batch(golden["syn_codes"][:8])
+    assert e.value.code == cab.CAB_EINVAL and "bf16" in str(e.value)
