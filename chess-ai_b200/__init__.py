@@ -61,6 +61,14 @@ _SIGS = {
     "cab_eval_host": [_vp, _vp, C.c_long, _vp],
     "cab_eval_dev": [_vp, _vp, C.c_long, _vp, _vp],
     "cab_eval_dev_batches": [_vp, _vp, C.c_long, C.c_long, _vp, C.POINTER(_vp), C.c_int],
+    "cab_leafq_create": [_vp, C.c_long, C.c_long, C.c_int, C.POINTER(_vp)],
+    "cab_leafq_destroy": [_vp],
+    "cab_leafq_push": [_vp, _i8p, C.c_long, _lp],
+    "cab_leafq_pending": [_vp, _lp],
+    "cab_leafq_flush": [_vp, _lp],
+    "cab_leafq_results": [_vp, C.POINTER(_dp)],
+    "cab_leafq_stats": [_vp, _lp, _lp, _lp],
+    "cab_prior_softmax_host": [C.c_int, _f64p, _i32p, C.c_int, _f64p, _f64p],
     "cab_eval_bf16_dev": [_vp, _vp, C.c_long, _vp, _vp],
     "cab_eval_bf16_host": [_vp, _i8p, C.c_long, _f64p],
     "cab_eval_records_host": [_vp, _u8p, C.c_long, _f64p],

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libchessai_b200.so")
-SOURCES = ["cab_api.cu", "cab_train.cu", "cab_tc.cu"]
+SOURCES = ["cab_api.cu", "cab_train.cu", "cab_tc.cu", "cab_leafq.cu"]
 HEADERS = ["cab_internal.cuh", "mlp_stream_kernel.cuh", "train_kernels.cuh", os.path.join("..", "..", "include", "chessai_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -1,0 +1,173 @@
+// cab_leafq.cu — the MCTS leaf queue and K7, the prior softmax.
+//
+// The reference evaluates ONE board per node expansion inside Decider::prediction
+// (/root/reference/src/mcts_network/decider.cpp:31-61, called from tree.cpp:295). With virtual loss the search keeps
+// many playouts in flight, so expansions of many trees / games pile up here and are evaluated thousands per launch:
+//   worker threads  cab_leafq_push(codes)        -> slot numbers (lock-free reservation, copy into pinned memory)
+//   any thread      cab_leafq_flush()            -> H2D in pieces, cab_eval launches of `batch` boards round-robin
+//                                                   over the queue's streams, D2H; results indexed by slot
+// K7: priors of a node's children, tree.cpp:299-306:  w_i = exp(cm * logit_i),  prior_i = w_i / sum_j w_j
+#include <atomic>
+#include <cstring>
+
+#include "cab_internal.cuh"
+
+namespace cab {
+int ensure_packed(cab_net *net, cudaStream_t stream);
+int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d_out, double *d_save, long save_stride,
+                   cudaStream_t stream);
+
+// one warp per segment (node); segments are short (a chess position has ~20-40 children)
+__global__ void __launch_bounds__(256) prior_softmax_kernel(const double *__restrict__ logits, const int *__restrict__ seg_off,
+                                                             int n_seg, const double *__restrict__ color_mult,
+                                                             double *__restrict__ priors) {
+  const int seg = (int) ((blockIdx.x * (long) blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (seg >= n_seg) return;
+  const int lo = seg_off[seg], hi = seg_off[seg + 1];
+  const double cm = color_mult[seg];
+  double sum = 0.0;
+  for (int i = lo + lane; i < hi; i += 32) sum += exp(cm * logits[i]);       // tree.cpp:302-303
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int i = lo + lane; i < hi; i += 32) priors[i] = exp(cm * logits[i]) / sum;  // Node::expand, tree.cpp:92
+}
+}  // namespace cab
+
+struct cab_leafq {
+  cab_net *net = nullptr;
+  long capacity = 0, batch = 4096;
+  int n_streams = 4;
+  int8_t *h_codes = nullptr;   // pinned [capacity][64]
+  double *h_out = nullptr;     // pinned [capacity]
+  int8_t *d_codes = nullptr;
+  double *d_out = nullptr;
+  std::vector<cudaStream_t> streams;
+  std::vector<cudaEvent_t> events;
+  std::atomic<long> head{0};
+  long launches = 0, flushes = 0, evaluated = 0;
+};
+
+using namespace cab;
+
+extern "C" {
+
+int cab_leafq_create(cab_net *net, long capacity, long batch, int n_streams, cab_leafq **out) {
+  if (!net || !out || capacity <= 0 || batch <= 0 || n_streams <= 0 || n_streams > 32) { set_error("bad argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  cab_leafq *q = new cab_leafq();
+  q->net = net; q->capacity = capacity; q->batch = batch; q->n_streams = n_streams;
+  CAB_CUDA(cudaMallocHost(&q->h_codes, capacity * 64));
+  CAB_CUDA(cudaMallocHost(&q->h_out, capacity * sizeof(double)));
+  CAB_CUDA(cudaMalloc(&q->d_codes, capacity * 64));
+  CAB_CUDA(cudaMalloc(&q->d_out, capacity * sizeof(double)));
+  q->streams.resize(n_streams);
+  q->events.resize(n_streams);
+  for (int i = 0; i < n_streams; ++i) {
+    CAB_CUDA(cudaStreamCreateWithFlags(&q->streams[i], cudaStreamNonBlocking));
+    CAB_CUDA(cudaEventCreateWithFlags(&q->events[i], cudaEventDisableTiming));
+  }
+  *out = q;
+  return CAB_OK;
+}
+
+int cab_leafq_destroy(cab_leafq *q) {
+  if (!q) return CAB_OK;
+  cudaSetDevice(q->net->device);
+  for (auto s : q->streams) cudaStreamDestroy(s);
+  for (auto e : q->events) cudaEventDestroy(e);
+  cudaFreeHost(q->h_codes); cudaFreeHost(q->h_out); cudaFree(q->d_codes); cudaFree(q->d_out);
+  delete q;
+  return CAB_OK;
+}
+
+// Thread-safe. Reserves n consecutive slots and copies the boards in; *first_slot is the ticket for the results.
+// CAB_ESTATE when the queue is full (flush first).
+int cab_leafq_push(cab_leafq *q, const int8_t *codes, long n, long *first_slot) {
+  if (!q || !codes || n <= 0 || !first_slot) { set_error("bad argument"); return CAB_EINVAL; }
+  const long at = q->head.fetch_add(n);
+  if (at + n > q->capacity) {
+    q->head.fetch_sub(n);
+    set_error("leaf queue full (%ld + %ld > %ld): flush it", at, n, q->capacity);
+    return CAB_ESTATE;
+  }
+  memcpy(q->h_codes + at * 64, codes, (size_t) n * 64);
+  *first_slot = at;
+  return CAB_OK;
+}
+
+int cab_leafq_pending(cab_leafq *q, long *n) {
+  if (!q || !n) { set_error("null argument"); return CAB_EINVAL; }
+  *n = q->head.load();
+  return CAB_OK;
+}
+
+// Not concurrent with push. Evaluates slots [0, pending) and empties the queue.
+int cab_leafq_flush(cab_leafq *q, long *n_evaluated) {
+  if (!q) { set_error("null argument"); return CAB_EINVAL; }
+  const long n = q->head.load();
+  if (n_evaluated) *n_evaluated = n;
+  if (n == 0) return CAB_OK;
+  cab_net *net = q->net;
+  CAB_CUDA(cudaSetDevice(net->device));
+  {
+    std::lock_guard<std::mutex> lk(net->mu);
+    int rc = ensure_packed(net, q->streams[0]);
+    if (rc != CAB_OK) return rc;
+    CAB_CUDA(cudaStreamSynchronize(q->streams[0]));
+  }
+  int i = 0;
+  for (long b0 = 0; b0 < n; b0 += q->batch, ++i) {
+    const long nb = std::min(q->batch, n - b0);
+    cudaStream_t s = q->streams[i % q->n_streams];
+    CAB_CUDA(cudaMemcpyAsync(q->d_codes + b0 * 64, q->h_codes + b0 * 64, nb * 64, cudaMemcpyHostToDevice, s));
+    int rc = launch_forward(net, q->d_codes + b0 * 64, nb, q->d_out + b0, nullptr, 0, s);
+    if (rc != CAB_OK) return rc;
+    CAB_CUDA(cudaMemcpyAsync(q->h_out + b0, q->d_out + b0, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ++q->launches;
+  }
+  for (auto s : q->streams) CAB_CUDA(cudaStreamSynchronize(s));
+  ++q->flushes;
+  q->evaluated += n;
+  q->head.store(0);
+  return CAB_OK;
+}
+
+// results of the last flush, indexed by slot; valid until the next push
+int cab_leafq_results(cab_leafq *q, const double **results) {
+  if (!q || !results) { set_error("null argument"); return CAB_EINVAL; }
+  *results = q->h_out;
+  return CAB_OK;
+}
+
+int cab_leafq_stats(cab_leafq *q, long *launches, long *flushes, long *evaluated) {
+  if (!q) { set_error("null argument"); return CAB_EINVAL; }
+  if (launches) *launches = q->launches;
+  if (flushes) *flushes = q->flushes;
+  if (evaluated) *evaluated = q->evaluated;
+  return CAB_OK;
+}
+
+// K7 on host arrays: n_seg nodes, node s owns logits[seg_off[s] .. seg_off[s+1]) and colour multiplier color_mult[s]
+int cab_prior_softmax_host(int device, const double *logits, const int *seg_off, int n_seg, const double *color_mult,
+                           double *priors_out) {
+  if (n_seg < 0 || (n_seg > 0 && (!logits || !seg_off || !color_mult || !priors_out))) { set_error("bad argument"); return CAB_EINVAL; }
+  if (n_seg == 0) return CAB_OK;
+  CAB_CUDA(cudaSetDevice(device));
+  const int total = seg_off[n_seg];
+  double *d_l = nullptr, *d_p = nullptr, *d_c = nullptr;
+  int *d_o = nullptr;
+  CAB_CUDA(cudaMalloc(&d_l, (size_t) std::max(total, 1) * sizeof(double)));
+  CAB_CUDA(cudaMalloc(&d_p, (size_t) std::max(total, 1) * sizeof(double)));
+  CAB_CUDA(cudaMalloc(&d_c, (size_t) n_seg * sizeof(double)));
+  CAB_CUDA(cudaMalloc(&d_o, (size_t) (n_seg + 1) * sizeof(int)));
+  CAB_CUDA(cudaMemcpy(d_l, logits, (size_t) total * sizeof(double), cudaMemcpyHostToDevice));
+  CAB_CUDA(cudaMemcpy(d_c, color_mult, (size_t) n_seg * sizeof(double), cudaMemcpyHostToDevice));
+  CAB_CUDA(cudaMemcpy(d_o, seg_off, (size_t) (n_seg + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  prior_softmax_kernel<<<(n_seg * 32 + 255) / 256, 256>>>(d_l, d_o, n_seg, d_c, d_p);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(priors_out, d_p, (size_t) total * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_l); cudaFree(d_p); cudaFree(d_c); cudaFree(d_o);
+  if (e != cudaSuccess) return cuda_fail(e, "prior_softmax", __FILE__, __LINE__);
+  return CAB_OK;
+}
+
+}  // extern "C"

@@ -94,6 +94,23 @@ CAB_API int cab_eval_records_host(cab_net *net, const uint8_t *records_host, lon
  * acts_host receives n_boards * sum(dims[1..]) doubles, board-major, layers concatenated in order. */
 CAB_API int cab_forward_full_host(cab_net *net, const int8_t *codes_host, long n_boards, double *acts_host);
 
+/* ---- MCTS leaf queue with virtual-loss batching (new; sits in front of Decider::prediction, tree.cpp:295) --------- */
+/* Search threads park a playout at an unexpanded node (virtual loss on its path), push the boards they need
+ * evaluated and go on with other playouts / trees; one flush evaluates everything queued in launches of `batch`
+ * boards over `n_streams` streams. push is thread-safe and lock-free; flush / results are single-threaded. */
+typedef struct cab_leafq cab_leafq;
+CAB_API int cab_leafq_create(cab_net *net, long capacity, long batch, int n_streams, cab_leafq **out);
+CAB_API int cab_leafq_destroy(cab_leafq *q);
+CAB_API int cab_leafq_push(cab_leafq *q, const int8_t *codes, long n_boards, long *first_slot);
+CAB_API int cab_leafq_pending(cab_leafq *q, long *n_boards);
+CAB_API int cab_leafq_flush(cab_leafq *q, long *n_evaluated);
+CAB_API int cab_leafq_results(cab_leafq *q, const double **results_by_slot);
+CAB_API int cab_leafq_stats(cab_leafq *q, long *launches, long *flushes, long *evaluated);
+/* K7 — priors of expanded nodes (MCTS::expand_node, tree.cpp:299-306 + Node::expand :92): node s owns
+ * logits[seg_off[s] .. seg_off[s+1]); prior_i = exp(cm_s * logit_i) / sum over the node. */
+CAB_API int cab_prior_softmax_host(int device, const double *logits, const int *seg_off, int n_seg, const double *color_mult,
+                                   double *priors_out);
+
 /* ---- bf16 tensor-core forward (tcgen05 + TMEM + TMA) for WIDE networks ------------------------------------------ */
 /* Same forward (network.cpp:92-117) with bf16 operands, fp32 accumulation in tensor memory and f() in fp32. Only for
  * networks whose hidden widths are multiples of 256 (e.g. Network({2048,2048,2048,2048})); CAB_EINVAL otherwise.

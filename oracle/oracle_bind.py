@@ -191,6 +191,9 @@ class PortOracle:
         L.orc_net_load.argtypes = [C.c_char_p]
         L.orc_fnv1a64_file.restype = C.c_uint64
         L.orc_fnv1a64_file.argtypes = [C.c_char_p]
+        L.orc_prior_softmax.argtypes = [_f64p, C.c_int, C.c_double, _f64p]
+        L.orc_puct.restype = C.c_double
+        L.orc_puct.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
         L.orc_parse_case_file.restype = C.c_int
         L.orc_parse_case_file.argtypes = [C.c_char_p, _u8p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
 
@@ -228,6 +231,13 @@ class PortOracle:
     def philox(self, ctr, key):
         out = np.zeros(4, dtype=np.uint32)
         self.lib.orc_philox4x32_10(*[int(x) for x in ctr], *[int(x) for x in key], out)
+        return out
+
+    # -- search math
+    def prior_softmax(self, logits, color_multiplier):
+        l = np.ascontiguousarray(logits, dtype=np.float64)
+        out = np.zeros_like(l)
+        self.lib.orc_prior_softmax(l, len(l), color_multiplier, out)
         return out
 
     # -- encoder / formats
