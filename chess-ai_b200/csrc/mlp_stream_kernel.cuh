@@ -114,6 +114,16 @@ __device__ __forceinline__ void dispatch_chunk(int nbh, bool act_in, double (&ac
   }
 }
 #undef CAB_NB_CASE
+// f() on accumulator tiles 4G .. 4G+3 in place (8 independent activations in flight per lane)
+template <int G>
+__device__ __forceinline__ void act_group(double (&acc)[kMaxNBH][2], const double *tbl) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    acc[4 * G + u][0] = act_f_tbl(acc[4 * G + u][0], tbl);
+    acc[4 * G + u][1] = act_f_tbl(acc[4 * G + u][1], tbl);
+  }
+}
+
 #define CAB_NB_CASE(N) \
   case N: store_acc<N>(acc, a_out, lane); break;
 __device__ __forceinline__ void dispatch_store(int nbh, const double (&acc)[kMaxNBH][2], double2 *a_out, int lane) {
@@ -125,6 +135,19 @@ __device__ __forceinline__ void dispatch_store(int nbh, const double (&acc)[kMax
   }
 }
 #undef CAB_NB_CASE
+
+// Which warp of a pair is "half 0", and how a block of nb output tiles is split between the halves.
+//  * halves are interleaved over the SM sub-partitions (warp w sits on SMSP w % 4): with half = w & 1, SMSPs 0 and 2
+//    would host only half-0 warps and carry every layer's odd tile
+//  * the odd tile of a layer goes to half (layer & 1), so the halves' totals balance over the network
+//    (default net: 527 vs 529 tile-units per pass instead of 558 vs 498)
+__device__ __forceinline__ int pair_half(int warp) { return (warp ^ (warp >> 2)) & 1; }
+__device__ __forceinline__ void split_tiles(int nb, int layer, int half, int &j0, int &nbh) {
+  const int small = nb >> 1, big = nb - small;
+  const int share0 = (layer & 1) == 0 ? big : small;   // tiles of half 0 (first in the block)
+  j0 = half ? share0 : 0;
+  nbh = half ? nb - share0 : share0;
+}
 
 constexpr int kSmemChunks = 96;  // chunk descriptors cached in shared memory (default net: 21); longer plans read L2
 
@@ -170,7 +193,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
   uint32_t *done = reinterpret_cast<uint32_t *>(full + n_stages);  // arrivals per ring slot, monotonically increasing
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = warp >> 1, half = warp & 1;
+  const int pair = warp >> 1, half = pair_half(warp);
   // chunks this CTA will consume, in order: (groups it owns) x n_chunks
   const long my_groups = args.n_groups > blockIdx.x ? (args.n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long total_chunks = my_groups * args.n_chunks;
@@ -232,8 +255,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
       CAB_PROF_T(t_desc)
       const ChunkDesc d = chunks[c];
       const bool first = d.flags & kFirst, last = d.flags & kLast;
-      const int nb0 = (d.nb + 1) >> 1;                     // tiles of half 0; half 1 takes the rest
-      const int j0 = half ? nb0 : 0, nbh = half ? d.nb - nb0 : nb0;
+      int j0, nbh;
+      split_tiles(d.nb, d.layer, half, j0, nbh);
       if (first) {
 #pragma unroll
         for (int j = 0; j < kMaxNBH; ++j) acc[j][0] = acc[j][1] = 0.0;
@@ -243,7 +266,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
       mbar_wait(&full[rs], rk & 1);
       CAB_PROF_ACC(2, t_wait)
       CAB_PROF_T(t_mma)
-      double *save_row = (JIT && half == 0 && save_lane != nullptr) ? save_lane + (size_t) (d.save_in + d.t0) * args.save_stride : nullptr;
+      double *save_row = (JIT && j0 == 0 && nbh > 0 && save_lane != nullptr) ? save_lane + (size_t) (d.save_in + d.t0) * args.save_stride : nullptr;
       dispatch_chunk(nbh, JIT && (d.flags & kActIn), acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
                      ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount,
                      exp_tbl, save_row, args.save_stride);
@@ -270,43 +293,38 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
 
       CAB_PROF_T(t_act)
       if (last) {
-        // layer boundary: (1) both warps are done READING the layer input, (2) each writes a = f(theta) for its own
-        // tiles in place (a lane only ever touches the units it wrote itself), (3) outputs visible to the partner
+        // Layer boundary. (1) a = f(theta) on this warp's own tiles, IN REGISTERS and BEFORE the barrier: the wait for
+        // the partner (who may still be reading the layer input that the outputs overwrite in place) is spent on the
+        // exp / reciprocal math, and there is no shared-memory round trip. The 4-case switch gives the rolled loop
+        // static register indices; tiles past nbh hold zeros and f(0) = 0. (2) barrier: input fully read.
+        // (3) store the activations in place. (4) barrier: outputs visible to the partner.
         double2 *a_out = abuf + (size_t) (d.a_out + j0) * 32;
+        if (!JIT) {
+          for (int g4 = 0; g4 * 4 < nbh; ++g4) {
+            switch (g4) {
+              case 0: act_group<0>(acc, exp_tbl); break;
+              case 1: act_group<1>(acc, exp_tbl); break;
+              case 2: act_group<2>(acc, exp_tbl); break;
+              default: act_group<3>(acc, exp_tbl); break;
+            }
+          }
+        }
         CAB_PROF_T(t_bar1)
         pair_barrier(pair);
         CAB_PROF_ACC(7, t_bar1)
         dispatch_store(nbh, acc, a_out, lane);
-        int j = JIT ? nbh : 0;   // JIT: the raw pre-activations stay in the buffer; the consumer applies f()
-        if (JIT && (d.flags & kFinal) && half == 0) {
+        const bool owns_tile0 = j0 == 0 && nbh > 0;
+        if (JIT && (d.flags & kFinal) && owns_tile0) {   // JIT: raw pre-activations stay in the buffer; only the output is activated here
           double2 v = a_out[lane];
           v.x = act_f_tbl(v.x, exp_tbl);
           v.y = act_f_tbl(v.y, exp_tbl);
           a_out[lane] = v;
           if (save_lane != nullptr) *reinterpret_cast<double2 *>(save_lane + (size_t) d.save_off * args.save_stride) = v;
         }
-        for (; j + 4 <= nbh; j += 4) {   // 4 units = 8 independent activations in flight per lane
-          double2 v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = a_out[(j + u) * 32 + lane];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) { v[u].x = act_f_tbl(v[u].x, exp_tbl); v[u].y = act_f_tbl(v[u].y, exp_tbl); }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            a_out[(j + u) * 32 + lane] = v[u];
-            if (save_lane != nullptr)
-              *reinterpret_cast<double2 *>(save_lane + (size_t) (d.save_off + d.tile0 + j0 + j + u) * args.save_stride) = v[u];
-          }
-        }
-        for (; j < nbh; ++j) {
-          double2 v = a_out[j * 32 + lane];
-          v.x = act_f_tbl(v.x, exp_tbl);
-          v.y = act_f_tbl(v.y, exp_tbl);
-          a_out[j * 32 + lane] = v;
-          if (save_lane != nullptr)
-            *reinterpret_cast<double2 *>(save_lane + (size_t) (d.save_off + d.tile0 + j0 + j) * args.save_stride) = v;
-        }
-        if ((d.flags & kFinal) && half == 0 && args.out != nullptr && valid && q == 0) args.out[board] = a_out[lane].x;
+        if (!JIT && save_lane != nullptr)                // K2: keep every layer's activations for the backward pass
+          for (int j = 0; j < nbh; ++j)
+            *reinterpret_cast<double2 *>(save_lane + (size_t) (d.save_off + d.tile0 + j0 + j) * args.save_stride) = a_out[j * 32 + lane];
+        if ((d.flags & kFinal) && owns_tile0 && args.out != nullptr && valid && q == 0) args.out[board] = a_out[lane].x;
         CAB_PROF_T(t_bar2)
         pair_barrier(pair);
         CAB_PROF_ACC(7, t_bar2)

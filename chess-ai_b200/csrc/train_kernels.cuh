@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
   uint32_t *done = reinterpret_cast<uint32_t *>(full + n_stages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = warp >> 1, half = warp & 1;
+  const int pair = warp >> 1, half = pair_half(warp);
   const long my_groups = args.n_groups > blockIdx.x ? (args.n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long total_chunks = my_groups * args.n_chunks;
   const bool table_in_smem = args.n_chunks <= kSmemChunks;
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
     for (int c = 0; c < args.n_chunks; ++c, ++n) {
       const ChunkDesc d = chunks[c];
       const bool first = d.flags & kFirst, last = d.flags & kLast;
-      const int nb0 = (d.nb + 1) >> 1;
-      const int j0 = half ? nb0 : 0, nbh = half ? d.nb - nb0 : nb0;
+      int j0, nbh;
+      split_tiles(d.nb, d.layer, half, j0, nbh);
       if (first) {
 #pragma unroll
         for (int j = 0; j < kMaxNBH; ++j) acc[j][0] = acc[j][1] = 0.0;
