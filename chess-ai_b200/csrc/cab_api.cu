@@ -412,13 +412,13 @@ void release_ctx(cab_net *net, EvalCtx *c) {
   c->busy = false;
 }
 
-constexpr long kEvalChunkBoards = 131072;  // host<->device pipelining granularity of the *_host entry points
+constexpr long kEvalChunkBoards = 32768;  // host<->device pipelining granularity of the *_host entry points
 
 static int ctx_reserve(EvalCtx *c, long boards, bool records) {
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < kCtxStreams; ++i)
     if (c->stream[i] == nullptr) CAB_CUDA(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
   if (boards > c->cap_boards) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kCtxStreams; ++i) {
       cudaFree(c->d_codes[i]); cudaFree(c->d_out[i]); cudaFree(c->d_records[i]);
       c->d_records[i] = nullptr;
       CAB_CUDA(cudaMalloc(&c->d_codes[i], boards * 64));
@@ -427,7 +427,7 @@ static int ctx_reserve(EvalCtx *c, long boards, bool records) {
     c->cap_boards = boards;
   }
   if (records)
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kCtxStreams; ++i)
       if (c->d_records[i] == nullptr) CAB_CUDA(cudaMalloc(&c->d_records[i], c->cap_boards * 192));
   return CAB_OK;
 }
@@ -445,7 +445,7 @@ static int eval_host_impl(cab_net *net, const int8_t *codes, const uint8_t *reco
       if (rc == CAB_OK && cudaStreamSynchronize(c->stream[0]) != cudaSuccess) rc = CAB_ECUDA;
     }
     int i = 0;
-    for (long b0 = 0; b0 < n && rc == CAB_OK; b0 += chunk, i ^= 1) {
+    for (long b0 = 0; b0 < n && rc == CAB_OK; b0 += chunk, i = (i + 1) % kCtxStreams) {
       const long nb = std::min(chunk, n - b0);
       cudaStream_t s = c->stream[i];
       if (records != nullptr) {
@@ -458,7 +458,7 @@ static int eval_host_impl(cab_net *net, const int8_t *codes, const uint8_t *reco
       if (rc == CAB_OK) rc = launch_forward(net, c->d_codes[i], nb, c->d_out[i], nullptr, 0, s);
       if (rc == CAB_OK && cudaMemcpyAsync(out + b0, c->d_out[i], nb * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = CAB_ECUDA;
     }
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < kCtxStreams; ++k)
       if (cudaStreamSynchronize(c->stream[k]) != cudaSuccess && rc == CAB_OK) rc = CAB_ECUDA;
     if (rc == CAB_ECUDA) set_error("CUDA failure in eval: %s", cudaGetErrorString(cudaGetLastError()));
   }
@@ -497,7 +497,7 @@ int cab_net_destroy(cab_net *net) {
   cab_dp_shutdown(net);
   tc_free(net);
   for (EvalCtx *c : net->ctxs) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kCtxStreams; ++i) {
       if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
       cudaFree(c->d_codes[i]); cudaFree(c->d_out[i]); cudaFree(c->d_records[i]);
     }

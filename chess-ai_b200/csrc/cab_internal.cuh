@@ -69,11 +69,12 @@ struct StreamPlan {  // host description of one packed stream
   double *d_pack = nullptr;
 };
 
+constexpr int kCtxStreams = 4;  // H2D / kernel / D2H of consecutive chunks overlap across these
 struct EvalCtx {  // per-caller scratch: lets many host threads evaluate on one net concurrently
-  cudaStream_t stream[2] = {nullptr, nullptr};
-  int8_t *d_codes[2] = {nullptr, nullptr};
-  double *d_out[2] = {nullptr, nullptr};
-  uint8_t *d_records[2] = {nullptr, nullptr};
+  cudaStream_t stream[kCtxStreams] = {};
+  int8_t *d_codes[kCtxStreams] = {};
+  double *d_out[kCtxStreams] = {};
+  uint8_t *d_records[kCtxStreams] = {};
   long cap_boards = 0;
   bool busy = false;
 };
