@@ -109,6 +109,8 @@ struct cab_net {
   long tbuf_cap = 0;
   double *d_scalars = nullptr; // small device scratch (lambda, flags ...)
   cudaStream_t train_stream = nullptr;
+  cudaStream_t aux_stream[4] = {};  // helper streams for fanned-out passes (cab_train.cu:fan_out)
+  cudaEvent_t aux_event[5] = {};
   // data parallel
   void *nccl_comm = nullptr;
   int dp_rank = 0, dp_world = 1;

@@ -328,19 +328,33 @@ __global__ void __launch_bounds__(128) grad_kernel(const GradArgs args) {
     for (int j = 0; j < kGN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   // lane (r = lane>>2, c = lane&3): A[k = 8kt + r][board b + c], B[board b + c][n = 8nt + r]
   const size_t lane_off = (size_t) (lane & 3) * 8 + (lane >> 2);
+  // fragment pointers of this lane (unused tile slots point at slot 0 and are multiplied into nothing)
+  const double *ap[kGK], *bp[kGN];
+#pragma unroll
+  for (int i = 0; i < kGK; ++i) ap[i] = args.acts + (size_t) (t.a_unit + (i < t.nkt ? i : 0)) * args.save_stride + lane_off;
+#pragma unroll
+  for (int j = 0; j < kGN; ++j) bp[j] = args.psis + (size_t) (t.p_unit + (j < t.nnt ? j : 0)) * args.save_stride + lane_off;
+  // software pipeline: the 12 fragment loads of step b+4 are in flight while the 32 DMMAs of step b issue
+  double af[kGK], bf[kGN], an[kGK], bn[kGN];
+#pragma unroll
+  for (int i = 0; i < kGK; ++i) af[i] = __ldg(ap[i] + (size_t) b_lo * 8);
+#pragma unroll
+  for (int j = 0; j < kGN; ++j) bf[j] = __ldg(bp[j] + (size_t) b_lo * 8);
   for (long b = b_lo; b < b_hi; b += 4) {
-    double af[kGK], bf[kGN];
+    const long nb = b + 4 < b_hi ? b + 4 : b;
 #pragma unroll
-    for (int i = 0; i < kGK; ++i)
-      af[i] = i < t.nkt ? __ldg(args.acts + (size_t) (t.a_unit + i) * args.save_stride + (size_t) b * 8 + lane_off) : 0.0;
+    for (int i = 0; i < kGK; ++i) an[i] = __ldg(ap[i] + (size_t) nb * 8);
 #pragma unroll
-    for (int j = 0; j < kGN; ++j)
-      bf[j] = j < t.nnt ? __ldg(args.psis + (size_t) (t.p_unit + j) * args.save_stride + (size_t) b * 8 + lane_off) : 0.0;
+    for (int j = 0; j < kGN; ++j) bn[j] = __ldg(bp[j] + (size_t) nb * 8);
 #pragma unroll
     for (int i = 0; i < kGK; ++i)
 #pragma unroll
       for (int j = 0; j < kGN; ++j)
         if (i < t.nkt && j < t.nnt) dmma884(acc[i][j], af[i], bf[j]);
+#pragma unroll
+    for (int i = 0; i < kGK; ++i) af[i] = an[i];
+#pragma unroll
+    for (int j = 0; j < kGN; ++j) bf[j] = bn[j];
   }
   // C[row = lane>>2][col = 2*(lane&3) + {0,1}] -> G[k][n]
 #pragma unroll
