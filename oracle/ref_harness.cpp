@@ -17,7 +17,9 @@
 #include <atomic>
 #include <chrono>
 #include <cstdint>
+#include <cmath>
 #include <cstring>
+#include <random>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -273,3 +275,84 @@ int ref_prediction_file(void *net, const char *board_path, int white_to_move, do
 }
 
 }  // extern "C"
+
+// ---- rules engine: recorded random games (golden data for the fast move generator) ----------
+// Plays one game with the reference's own Game / Board / Move code from the given start-position file. At every ply
+// records the board as codes, the side to move, the full legal move list in the reference's generation order
+// (game.cpp:228-263: from-square ascending, to-square ascending, promotions Q,R,N,B) and the move played. Moves are
+// chosen at random with a bias towards castling, en passant, double steps and promotions so the rare rules are covered.
+// Layout of `moves_out`: per move 5 ints (r1, c1, r2, c2, promotion code: 0 none, 3 Q, 4 R, 6 N, 7 B).
+// Returns the number of plies recorded; *result_out = GameResult::evaluate(), *over_out = isOver().
+extern "C" int ref_record_game(const char *start_path, unsigned seed, int max_plies, int8_t *codes_out, int8_t *side_out,
+                               int *n_moves_out, int *moves_out, int moves_cap, int *chosen_out, int *nocap_out,
+                               int *result_out, int *over_out) {
+  auto *blank = new game::Game(8, 8);
+  blank->board()->loadFromFile(start_path);
+  game::Game *g = blank->clone();
+  std::mt19937 rng(seed);
+  int ply = 0, mpos = 0;
+  auto promo_code = [](piece::PieceType t) -> int {
+    if (t.isQueen()) return 3;
+    if (t.isRook()) return 4;
+    if (t.isKnight()) return 6;
+    if (t.isBishop()) return 7;
+    return 0;
+  };
+  while (ply < max_plies && !g->isOver()) {
+    std::vector<piece::Piece *> pcs = g->board()->pieces();
+    for (int i = 0; i < 64; ++i) codes_out[ply * 64 + i] = (int8_t) std::lround(pcs[i]->code() * 2.5);
+    side_out[ply] = (int8_t) g->getCurrentColor().value();
+    nocap_out[ply] = g->_moves_since_last_capture;
+    std::vector<game::Move> moves = g->possibleMoves(g->getCurrentColor());
+    n_moves_out[ply] = (int) moves.size();
+    if (moves.empty() || mpos + (int) moves.size() > moves_cap) break;
+    std::vector<int> special;
+    for (size_t k = 0; k < moves.size(); ++k) {
+      const game::Move &m = moves[k];
+      int *o = moves_out + 5 * (mpos + (int) k);
+      o[0] = m.startingRow(); o[1] = m.startingColumn(); o[2] = m.endingRow(); o[3] = m.endingColumn();
+      o[4] = promo_code(m.pawn_promotion_type());
+      piece::Piece *p = g->board()->getPiece(o[0], o[1]);
+      const bool pawn = p->type().isPawn();
+      const bool castle = p->type().isKing() && std::abs(o[1] - o[3]) == 2;
+      const bool ep = pawn && o[1] != o[3] && g->board()->getPiece(o[2], o[3])->type().isEmpty();
+      const bool dbl = pawn && std::abs(o[0] - o[2]) == 2;
+      if (castle || ep || o[4] != 0 || (dbl && rng() % 3 == 0)) special.push_back((int) k);
+    }
+    int pick;
+    if (!special.empty() && rng() % 2 == 0) pick = special[rng() % special.size()];
+    else pick = (int) (rng() % moves.size());
+    chosen_out[ply] = pick;
+    mpos += (int) moves.size();
+    if (!g->tryMove(moves[pick])) break;
+    ++ply;
+  }
+  // final position (after the last move) so the replay can check it too
+  std::vector<piece::Piece *> pcs = g->board()->pieces();
+  for (int i = 0; i < 64; ++i) codes_out[ply * 64 + i] = (int8_t) std::lround(pcs[i]->code() * 2.5);
+  side_out[ply] = (int8_t) g->getCurrentColor().value();
+  nocap_out[ply] = g->_moves_since_last_capture;
+  n_moves_out[ply] = (int) g->possibleMoves(g->getCurrentColor()).size();
+  *result_out = g->getResult().evaluate();
+  *over_out = g->isOver() ? 1 : 0;
+  return ply;
+}
+
+// perft on the reference engine (legal move generation + tryMove), for cross-checking node counts
+static long ref_perft_rec(game::Game *g, int depth) {
+  if (depth == 0) return 1;
+  if (g->isOver()) return 0;
+  long n = 0;
+  for (auto &m : g->possibleMoves(g->getCurrentColor())) {
+    game::Game *c = g->clone();
+    if (c->tryMove(m)) n += ref_perft_rec(c, depth - 1);
+    delete c;
+  }
+  return n;
+}
+extern "C" long ref_perft(const char *start_path, int depth) {
+  auto *blank = new game::Game(8, 8);
+  blank->board()->loadFromFile(start_path);
+  game::Game *g = blank->clone();
+  return ref_perft_rec(g, depth);
+}
