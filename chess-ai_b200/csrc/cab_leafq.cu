@@ -108,7 +108,7 @@ int cab_leafq_flush(cab_leafq *q, long *n_evaluated) {
   if (n == 0) return CAB_OK;
   cab_net *net = q->net;
   CAB_CUDA(cudaSetDevice(net->device));
-  {
+  if (net->pack_dirty) {  // weights changed since the last evaluation (rare): re-pack once, under the net's lock
     std::lock_guard<std::mutex> lk(net->mu);
     int rc = ensure_packed(net, q->streams[0]);
     if (rc != CAB_OK) return rc;

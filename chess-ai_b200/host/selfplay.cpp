@@ -1,0 +1,310 @@
+// selfplay.cpp — MCTS self-play with virtual-loss leaf batching on the B200 evaluator (BASELINE.json configs[2]).
+//
+// Many concurrent games per GPU; every host thread owns a slice of the games, its own trees and its own leaf queue
+// (cab_leafq_*), so threads never synchronise with each other and their GPU launches overlap. Per thread:
+//   repeat: start / resume playouts round-robin over its games; a playout that meets an unexpanded node puts a
+//           VIRTUAL LOSS on its path, pushes the node's board and all child boards (one contiguous push) and parks;
+//           when `in_flight` playouts are parked (or nothing else can start) ONE flush evaluates them all on the GPU,
+//           priors are formed, the parked playouts resume.
+// Search semantics = the reference's (/root/reference/src/mcts_network/tree.cpp, restated; integration/batched_mcts.cpp
+// proves the same scheduler equal to tree::MCTS::mcts() on the reference's rules code): PUCT :276-283, priors
+// exp(cm*logit)/sum :299-306, depth-limited playouts that expand on the way :202-262, leaf value = result or
+// sigmoid(material/27.18) :231-253, Dirichlet(0.2) noise mixed 25 % into the root priors :318-347, the move played is
+// the root child with the best PUCT score :195. Rules: host/fastchess.hpp (the reference's rules, verified move for move).
+// Child logits follow decider.cpp:43-58: network_priors = 0 keeps the shipped inverted branch (constant 20 unless the
+// opponent has no reply), 1 evaluates every child with the network.
+//
+//   selfplay <latest.txt> <games> <playouts_per_move> <moves_per_game> <threads> <in_flight_per_thread> <network_priors> [device] [seed]
+// Prints one JSON object. No CPU fallback: needs libchessai_b200.so and a GPU.
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <thread>
+#include <vector>
+
+#include "../../include/chessai_b200.h"
+#include "fastchess.hpp"
+
+using namespace fastchess;
+
+namespace {
+
+constexpr int kSearchDepth = 8;  // tree.cpp:145 SIMULATION_SEARCH_DEPTH
+
+struct Node {
+  double prior = 0.0, value_sum = 0.0;
+  int visits = 0, vloss = 0;
+  int first_child = -1;
+  uint16_t n_children = 0;
+  int8_t color = 1;
+  bool expanded = false;
+  Move move{0, 0, 0};
+  double value() const { const int n = visits - vloss; return n > 0 ? value_sum / n : 0.0; }
+};
+
+struct Playout {
+  Position pos;
+  int game = 0, node = 0, depth = 0;
+  int path[kSearchDepth + 2];
+  int path_len = 0;
+  long slot = -1;     // first queue slot of the pending expansion (parent board, then the children)
+  int n_pending = 0;  // children of the pending expansion
+  Move pending_moves[kMaxMoves];
+  bool child_eval[kMaxMoves];
+};
+
+struct GameState {
+  Position pos;
+  std::vector<Node> arena;
+  int launched = 0, done = 0, moves_played = 0;
+  bool finished = false;
+};
+
+struct Stats {
+  long playouts = 0, boards = 0, flushes = 0, expansions = 0, moves = 0, max_flush = 0;
+};
+
+struct Worker {
+  cab_net *net;
+  cab_leafq *q = nullptr;
+  std::vector<GameState> games;
+  int playouts_per_move, moves_per_game, in_flight;
+  bool network_priors;
+  std::mt19937_64 rng;
+  Stats st;
+
+  double puct(const Node &parent, const Node &child) const {
+    double base = std::log((parent.visits + 19652.0 + 1.0) / 19652.0) + 1.25;
+    base *= std::sqrt((double) parent.visits) / (child.visits + 1);
+    return base * child.prior + child.value();
+  }
+
+  void request_expansion(Playout &p) {
+    Move mv[kMaxMoves];
+    const int n = generate_moves(p.pos, p.pos.side, mv, /*queen_only=*/true);   // std::map<Move> keeps one promotion (Q8)
+    static thread_local int8_t buf[(kMaxMoves + 1) * 64];
+    std::memcpy(buf, p.pos.sq, 64);
+    int n_boards = 1;
+    for (int i = 0; i < n; ++i) {
+      Position c = p.pos;
+      apply_move(c.sq, mv[i]);
+      bool eval_child = network_priors;
+      if (!eval_child) {                       // decider.cpp:52-57: the network is asked only when the opponent has no reply
+        Move tmp[kMaxMoves];
+        c.side = (int8_t) -p.pos.side;
+        eval_child = generate_moves(c, c.side, tmp, true) == 0;
+      }
+      p.pending_moves[i] = mv[i];
+      p.child_eval[i] = eval_child;
+      if (eval_child) { std::memcpy(buf + n_boards * 64, c.sq, 64); ++n_boards; }
+    }
+    p.n_pending = n;
+    if (cab_leafq_push(q, buf, n_boards, &p.slot) != CAB_OK) { std::fprintf(stderr, "%s\n", cab_last_error()); std::exit(1); }
+    ++st.expansions;
+  }
+
+  void finish_expansion(Playout &p, const double *res) {
+    GameState &g = games[p.game];
+    Node &n = g.arena[p.node];
+    if (n.expanded) return;                    // a sibling playout parked on the same node got there first
+    const double cm = n.color;
+    const int k = p.n_pending;
+    const int first = (int) g.arena.size();
+    g.arena.resize(g.arena.size() + k);
+    Node &nn = g.arena[p.node];                // the resize may have moved the arena
+    double sum = 0.0;
+    long s = p.slot + 1;
+    for (int i = 0; i < k; ++i) {
+      const double logit = p.child_eval[i] ? cm * res[s++] : cm * 20.0;
+      const double w = std::exp(cm * logit);   // tree.cpp:302
+      g.arena[first + i].prior = w;
+      sum += w;
+    }
+    for (int i = 0; i < k; ++i) {
+      Node &c = g.arena[first + i];
+      c.prior /= sum;
+      c.color = (int8_t) -nn.color;
+      c.move = p.pending_moves[i];
+    }
+    nn.first_child = first;
+    nn.n_children = (uint16_t) k;
+    nn.expanded = true;
+    if (p.node == 0 && k > 0) {                // root: Dirichlet(0.2) noise, 25 % (tree.cpp:318-347)
+      std::gamma_distribution<double> gamma(0.2, 1.0);
+      std::vector<double> th(k);
+      double tot = 0.0;
+      for (auto &t : th) { t = gamma(rng); tot += t; }
+      for (int i = 0; i < k; ++i) g.arena[first + i].prior = g.arena[first + i].prior * 0.75 + (th[i] / tot) * 0.25;
+    }
+  }
+
+  // advance until the playout parks (false) or completes (true)
+  bool advance(Playout &p) {
+    GameState &g = games[p.game];
+    while (p.depth < kSearchDepth) {
+      if (p.pos.over) break;
+      Node &n = g.arena[p.node];
+      if (!n.expanded) {
+        request_expansion(p);
+        for (int i = 0; i < p.path_len; ++i) { g.arena[p.path[i]].visits += 1; g.arena[p.path[i]].vloss += 1; }
+        return false;
+      }
+      int best = -1;
+      double max_score = -1.0;
+      for (int i = 0; i < n.n_children; ++i) {
+        const double s = puct(n, g.arena[n.first_child + i]);
+        if (s > max_score) { max_score = s; best = n.first_child + i; }
+      }
+      if (best < 0) break;
+      play(p.pos, g.arena[best].move);
+      p.node = best;
+      p.path[p.path_len++] = best;
+      ++p.depth;
+    }
+    const double cc = p.pos.side;
+    double value;
+    if (p.pos.over) value = (cc * p.pos.result + 1.0) / 2.0;
+    else value = 1.0 / (1.0 + std::exp(-material(p.pos, p.pos.side) / 27.18));
+    for (int i = 0; i < p.path_len; ++i) {
+      Node &n = g.arena[p.path[i]];
+      n.visits += 1;
+      n.value_sum += std::fabs(cc == n.color ? value : 1.0 - value);
+    }
+    ++st.playouts;
+    return true;
+  }
+
+  void new_root(GameState &g) {
+    g.arena.clear();
+    g.arena.reserve(1 << 14);
+    g.arena.emplace_back();
+    g.arena[0].color = g.pos.side;
+    g.launched = g.done = 0;
+  }
+
+  void run() {
+    if (cab_leafq_create(net, 1 << 18, 4096, 2, &q) != CAB_OK) { std::fprintf(stderr, "%s\n", cab_last_error()); std::exit(1); }
+    for (auto &g : games) new_root(g);
+    std::vector<Playout> parked, still;
+    parked.reserve(in_flight);
+    bool active = true;
+    while (active) {
+      // launch new playouts round-robin
+      bool launched_any = true;
+      while (launched_any && (int) parked.size() < in_flight) {
+        launched_any = false;
+        for (size_t gi = 0; gi < games.size() && (int) parked.size() < in_flight; ++gi) {
+          GameState &g = games[gi];
+          if (g.finished || g.launched >= playouts_per_move) continue;
+          if (!g.arena[0].expanded && g.launched > g.done) continue;   // one playout until the root exists
+          Playout p;
+          p.pos = g.pos;
+          p.game = (int) gi;
+          p.node = 0;
+          p.path[0] = 0;
+          p.path_len = 1;
+          ++g.launched;
+          launched_any = true;
+          if (advance(p)) ++g.done;
+          else parked.push_back(p);
+        }
+      }
+      if (!parked.empty()) {
+        long n_eval = 0;
+        if (cab_leafq_flush(q, &n_eval) != CAB_OK) { std::fprintf(stderr, "%s\n", cab_last_error()); std::exit(1); }
+        const double *res = nullptr;
+        cab_leafq_results(q, &res);
+        ++st.flushes;
+        st.boards += n_eval;
+        st.max_flush = std::max(st.max_flush, n_eval);
+        for (auto &p : parked) {
+          GameState &g = games[p.game];
+          for (int i = 0; i < p.path_len; ++i) { g.arena[p.path[i]].visits -= 1; g.arena[p.path[i]].vloss -= 1; }
+          finish_expansion(p, res);
+        }
+        still.clear();
+        for (auto &p : parked) {
+          if (advance(p)) ++games[p.game].done;
+          else still.push_back(p);
+        }
+        parked.swap(still);
+      }
+      // games whose search is complete: play the move with the best PUCT score (tree.cpp:195) and start a new tree
+      active = false;
+      for (auto &g : games) {
+        if (g.finished) continue;
+        if (g.done >= playouts_per_move) {
+          const Node &root = g.arena[0];
+          int best = -1;
+          double max_score = -1.0;
+          for (int i = 0; i < root.n_children; ++i) {
+            const double s = puct(root, g.arena[root.first_child + i]);
+            if (s > max_score) { max_score = s; best = root.first_child + i; }
+          }
+          if (best >= 0) play(g.pos, g.arena[best].move);
+          ++g.moves_played;
+          ++st.moves;
+          if (best < 0 || g.pos.over || g.moves_played >= moves_per_game) g.finished = true;
+          else new_root(g);
+        }
+        if (!g.finished) active = true;
+      }
+    }
+    cab_leafq_destroy(q);
+  }
+};
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  if (argc < 8) {
+    std::fprintf(stderr, "usage: %s latest.txt games playouts_per_move moves_per_game threads in_flight_per_thread network_priors [device] [seed]\n", argv[0]);
+    return 2;
+  }
+  const int games = std::atoi(argv[2]), playouts = std::atoi(argv[3]), moves = std::atoi(argv[4]);
+  const int threads = std::max(1, std::atoi(argv[5])), in_flight = std::atoi(argv[6]);
+  const bool network_priors = std::atoi(argv[7]) != 0;
+  const int device = argc > 8 ? std::atoi(argv[8]) : 0;
+  const unsigned long long seed = argc > 9 ? std::strtoull(argv[9], nullptr, 10) : 1234;
+  cab_net *net = nullptr;
+  if (cab_net_load_text(argv[1], device, &net) != CAB_OK) { std::fprintf(stderr, "%s\n", cab_last_error()); return 1; }
+
+  std::vector<Worker> workers(threads);
+  for (int t = 0; t < threads; ++t) {
+    Worker &w = workers[t];
+    w.net = net;
+    w.playouts_per_move = playouts;
+    w.moves_per_game = moves;
+    w.in_flight = in_flight;
+    w.network_priors = network_priors;
+    w.rng.seed(seed + 7919ull * t);
+    const int lo = games * t / threads, hi = games * (t + 1) / threads;
+    w.games.resize(hi - lo);
+    for (auto &g : w.games) start_position(g.pos);
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> pool;
+  for (auto &w : workers) pool.emplace_back([&w] { w.run(); });
+  for (auto &th : pool) th.join();
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+  Stats tot;
+  for (auto &w : workers) {
+    tot.playouts += w.st.playouts; tot.boards += w.st.boards; tot.flushes += w.st.flushes;
+    tot.expansions += w.st.expansions; tot.moves += w.st.moves; tot.max_flush = std::max(tot.max_flush, w.st.max_flush);
+  }
+  long launches = 0;
+  cab_net_launch_count(net, &launches);
+  std::printf("{\"config\": \"MCTS self-play, virtual-loss leaf batching\", \"games\": %d, \"playouts_per_move\": %d, \"moves_per_game\": %d, "
+              "\"threads\": %d, \"in_flight_per_thread\": %d, \"network_priors\": %d, \"seconds\": %.3f, \"moves_played\": %ld, "
+              "\"playouts\": %ld, \"playouts_per_s\": %.1f, \"boards_evaluated\": %ld, \"boards_per_s\": %.1f, \"expansions\": %ld, "
+              "\"flushes\": %ld, \"avg_boards_per_flush\": %.1f, \"max_boards_per_flush\": %ld, \"gpu_launches\": %ld}\n",
+              games, playouts, moves, threads, in_flight, (int) network_priors, secs, tot.moves, tot.playouts, tot.playouts / secs,
+              tot.boards, tot.boards / secs, tot.expansions, tot.flushes, tot.flushes ? (double) tot.boards / tot.flushes : 0.0,
+              tot.max_flush, launches);
+  cab_net_destroy(net);
+  return 0;
+}
