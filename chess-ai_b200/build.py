@@ -43,18 +43,23 @@ def build(verbose=False, force=False):
         objs.append(obj)
     if force or _stale(LIB, objs):
         subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a"] + LINK + objs + ["-o", LIB])
-    # host-side C++ (g++): the fast rules engine (C entry points for the tests) and the self-play driver
+    # host-side C++ (g++): the fast rules engine (C entry points for the tests) and the self-play driver, the trainer
     host = os.path.join(HERE, "host")
     gxx = os.environ.get("CXX", "g++")
     fc = os.path.join(LIB_DIR, "libfastchess.so")
-    fc_deps = [os.path.join(host, "fastchess_c.cpp"), os.path.join(host, "fastchess.hpp")]
+    fc_deps = [os.path.join(host, "fastchess_c.cpp"), os.path.join(host, "fastchess.hpp"), os.path.join(host, "cases.hpp")]
     if force or _stale(fc, fc_deps):
         subprocess.check_call([gxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-static-libstdc++",
                                "-static-libgcc", "-o", fc, fc_deps[0]])
     sp = os.path.join(LIB_DIR, "selfplay")
-    sp_deps = [os.path.join(host, "selfplay.cpp"), os.path.join(host, "fastchess.hpp"), LIB]
+    sp_deps = [os.path.join(host, "selfplay.cpp"), os.path.join(host, "fastchess.hpp"), os.path.join(host, "cases.hpp"), LIB]
     if force or _stale(sp, sp_deps):
         subprocess.check_call([gxx, "-std=c++17", "-O2", "-pthread", "-static-libstdc++", "-static-libgcc", "-o", sp, sp_deps[0],
+                               "-L" + LIB_DIR, "-lchessai_b200", "-Wl,-rpath,$ORIGIN"])
+    tr = os.path.join(LIB_DIR, "train")
+    tr_deps = [os.path.join(host, "train.cpp"), os.path.join(host, "cases.hpp"), LIB]
+    if force or _stale(tr, tr_deps):
+        subprocess.check_call([gxx, "-std=c++17", "-O2", "-static-libstdc++", "-static-libgcc", "-o", tr, tr_deps[0],
                                "-L" + LIB_DIR, "-lchessai_b200", "-Wl,-rpath,$ORIGIN"])
     tool = os.path.join(LIB_DIR, "pipe_peaks")
     tsrc = os.path.join(CSRC, "tools", "pipe_peaks.cu")

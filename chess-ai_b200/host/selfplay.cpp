@@ -14,7 +14,12 @@
 // Child logits follow decider.cpp:43-58: network_priors = 0 keeps the shipped inverted branch (constant 20 unless the
 // opponent has no reply), 1 evaluates every child with the network.
 //
-//   selfplay <latest.txt> <games> <playouts_per_move> <moves_per_game> <threads> <in_flight_per_thread> <network_priors> [device] [seed]
+// Training cases (host/cases.hpp; make_cases.cpp:36-59, initialization.cpp:221-227): after every move the new board is
+// kept with probability save_ratio together with clamp(2*root_value-1); when the game ends each kept board gets the
+// target 10*(4*b + result)/5 and is appended to the packed shard `cases_path`.
+//
+//   selfplay <latest.txt> <games> <playouts_per_move> <moves_per_game> <threads> <in_flight_per_thread> <network_priors>
+//            [device] [seed] [cases_path] [save_ratio]
 // Prints one JSON object. No CPU fallback: needs libchessai_b200.so and a GPU.
 #include <atomic>
 #include <chrono>
@@ -26,6 +31,7 @@
 #include <vector>
 
 #include "../../include/chessai_b200.h"
+#include "cases.hpp"
 #include "fastchess.hpp"
 
 using namespace fastchess;
@@ -61,6 +67,7 @@ struct GameState {
   std::vector<Node> arena;
   int launched = 0, done = 0, moves_played = 0;
   bool finished = false;
+  std::vector<cases::Case> kept;   // boards of this game awaiting the game result
 };
 
 struct Stats {
@@ -73,6 +80,8 @@ struct Worker {
   std::vector<GameState> games;
   int playouts_per_move, moves_per_game, in_flight;
   bool network_priors;
+  double save_ratio = 0.0;
+  std::vector<cases::Case> finished_cases;
   std::mt19937_64 rng;
   Stats st;
 
@@ -247,8 +256,18 @@ struct Worker {
           if (best >= 0) play(g.pos, g.arena[best].move);
           ++g.moves_played;
           ++st.moves;
-          if (best < 0 || g.pos.over || g.moves_played >= moves_per_game) g.finished = true;
-          else new_root(g);
+          if (save_ratio > 0.0 && std::generate_canonical<double, 53>(rng) < save_ratio) {   // NetworkStorage::saveBoard
+            cases::Case c;
+            std::memcpy(c.codes, g.pos.sq, 64);
+            c.target = cases::bounded_mcts_result(root.value());
+            g.kept.push_back(c);
+          }
+          if (best < 0 || g.pos.over || g.moves_played >= moves_per_game) {
+            g.finished = true;
+            const double result = g.pos.over ? (double) g.pos.result : 0.0;   // GameResult::evaluate, game.fwd.h:82-95
+            for (auto &c : g.kept) { c.target = cases::overall_result(c.target, result); finished_cases.push_back(c); }
+            g.kept.clear();
+          } else new_root(g);
         }
         if (!g.finished) active = true;
       }
@@ -269,6 +288,8 @@ int main(int argc, char **argv) {
   const bool network_priors = std::atoi(argv[7]) != 0;
   const int device = argc > 8 ? std::atoi(argv[8]) : 0;
   const unsigned long long seed = argc > 9 ? std::strtoull(argv[9], nullptr, 10) : 1234;
+  const char *cases_path = argc > 10 ? argv[10] : nullptr;
+  const double save_ratio = cases_path ? (argc > 11 ? std::atof(argv[11]) : 0.1) : 0.0;
   cab_net *net = nullptr;
   if (cab_net_load_text(argv[1], device, &net) != CAB_OK) { std::fprintf(stderr, "%s\n", cab_last_error()); return 1; }
 
@@ -280,6 +301,7 @@ int main(int argc, char **argv) {
     w.moves_per_game = moves;
     w.in_flight = in_flight;
     w.network_priors = network_priors;
+    w.save_ratio = save_ratio;
     w.rng.seed(seed + 7919ull * t);
     const int lo = games * t / threads, hi = games * (t + 1) / threads;
     w.games.resize(hi - lo);
@@ -296,15 +318,21 @@ int main(int argc, char **argv) {
     tot.playouts += w.st.playouts; tot.boards += w.st.boards; tot.flushes += w.st.flushes;
     tot.expansions += w.st.expansions; tot.moves += w.st.moves; tot.max_flush = std::max(tot.max_flush, w.st.max_flush);
   }
+  long n_cases = 0;
+  if (cases_path)
+    for (auto &w : workers) {
+      if (!cases::append_shard(cases_path, w.finished_cases)) { std::fprintf(stderr, "cannot append to %s\n", cases_path); return 1; }
+      n_cases += (long) w.finished_cases.size();
+    }
   long launches = 0;
   cab_net_launch_count(net, &launches);
   std::printf("{\"config\": \"MCTS self-play, virtual-loss leaf batching\", \"games\": %d, \"playouts_per_move\": %d, \"moves_per_game\": %d, "
               "\"threads\": %d, \"in_flight_per_thread\": %d, \"network_priors\": %d, \"seconds\": %.3f, \"moves_played\": %ld, "
               "\"playouts\": %ld, \"playouts_per_s\": %.1f, \"boards_evaluated\": %ld, \"boards_per_s\": %.1f, \"expansions\": %ld, "
-              "\"flushes\": %ld, \"avg_boards_per_flush\": %.1f, \"max_boards_per_flush\": %ld, \"gpu_launches\": %ld}\n",
+              "\"flushes\": %ld, \"avg_boards_per_flush\": %.1f, \"max_boards_per_flush\": %ld, \"gpu_launches\": %ld, \"cases_written\": %ld}\n",
               games, playouts, moves, threads, in_flight, (int) network_priors, secs, tot.moves, tot.playouts, tot.playouts / secs,
               tot.boards, tot.boards / secs, tot.expansions, tot.flushes, tot.flushes ? (double) tot.boards / tot.flushes : 0.0,
-              tot.max_flush, launches);
+              tot.max_flush, launches, n_cases);
   cab_net_destroy(net);
   return 0;
 }

@@ -1,0 +1,140 @@
+// train.cpp — the trainer loop over packed case shards, with checkpoint rotation (SURVEY §8f N3 + N4).
+//
+// Reference: network::train::train_network (/root/reference/src/main/network/train.cpp:39-68): lambda0 = 2.0; draw a
+// case uniformly, Optimizer::optimize, when lambda leaves [1e-4, 10] reset it to 2.0 and dropout; every
+// GAMES_PER_NETWORK_SAVE cases NetworkStorage::saveNetwork (network.cpp:345-364): rename latest.txt -> gen-<N>.txt,
+// write the new latest.txt.
+//   mode "exact": that loop verbatim, one case per step, executed on the device by cab_train_sequence
+//   mode "batch": the minibatch extension (cab_train_batch_host), same lambda / dropout rule applied per step
+// Beyond the reference: lambda, the step count and the generation number persist in <out_dir>/trainer_state.txt, so a
+// restarted trainer continues instead of starting again at lambda0 and overwriting gen-0 (the reference loses both).
+//
+//   train <net_in.txt> <shard> <out_dir> <exact|batch> <steps> <batch> [device] [seed] [save_every]
+// Prints one JSON object. No CPU fallback.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/chessai_b200.h"
+#include "cases.hpp"
+
+namespace {
+
+struct TrainerState {
+  double lambda = 2.0;   // Optimizer::DEFAULT_INITIAL_LAMBDA, network.h:153
+  long steps = 0, resets = 0, generation = 0;
+};
+
+bool load_state(const std::string &path, TrainerState &s) {
+  FILE *f = std::fopen(path.c_str(), "r");
+  if (!f) return false;
+  const int n = std::fscanf(f, "%lf %ld %ld %ld", &s.lambda, &s.steps, &s.resets, &s.generation);
+  std::fclose(f);
+  return n == 4;
+}
+
+bool save_state(const std::string &path, const TrainerState &s) {
+  FILE *f = std::fopen(path.c_str(), "w");
+  if (!f) return false;
+  std::fprintf(f, "%.17e %ld %ld %ld\n", s.lambda, s.steps, s.resets, s.generation);
+  return std::fclose(f) == 0;
+}
+
+// NetworkStorage::saveNetwork: latest.txt becomes gen-<N>.txt, the current weights become latest.txt
+int rotate(cab_net *net, const std::string &dir, TrainerState &s) {
+  const std::string latest = dir + "/latest.txt";
+  FILE *probe = std::fopen(latest.c_str(), "r");
+  if (probe) {
+    std::fclose(probe);
+    const std::string past = dir + "/gen-" + std::to_string(s.generation++) + ".txt";
+    if (std::rename(latest.c_str(), past.c_str()) != 0) return CAB_EIO;
+  }
+  const int rc = cab_net_dump_text(net, latest.c_str());
+  if (rc != CAB_OK) return rc;
+  return save_state(dir + "/trainer_state.txt", s) ? CAB_OK : CAB_EIO;
+}
+
+#define CK(call) do { if ((call) != CAB_OK) { std::fprintf(stderr, "%s: %s\n", #call, cab_last_error()); return 1; } } while (0)
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  if (argc < 7) {
+    std::fprintf(stderr, "usage: %s net_in.txt shard out_dir exact|batch steps batch [device] [seed] [save_every]\n", argv[0]);
+    return 2;
+  }
+  const std::string net_in = argv[1], shard = argv[2], out_dir = argv[3], mode = argv[4];
+  const long steps = std::atol(argv[5]);
+  const long batch = mode == "exact" ? 1 : std::atol(argv[6]);
+  const int device = argc > 7 ? std::atoi(argv[7]) : 0;
+  const unsigned long long seed = argc > 8 ? std::strtoull(argv[8], nullptr, 10) : 5489;
+  const long save_every = argc > 9 ? std::atol(argv[9]) : 20;   // GAMES_PER_NETWORK_SAVE default, initialization.h:56
+  if ((mode != "exact" && mode != "batch") || steps <= 0 || batch <= 0 || save_every <= 0) { std::fprintf(stderr, "bad arguments\n"); return 2; }
+
+  std::vector<cases::Case> cs;
+  if (!cases::read_shard(shard, cs) || cs.empty()) { std::fprintf(stderr, "cannot read shard %s\n", shard.c_str()); return 1; }
+  TrainerState st;
+  const bool resumed = load_state(out_dir + "/trainer_state.txt", st);
+  cab_net *net = nullptr;
+  CK(cab_net_load_text(resumed ? (out_dir + "/latest.txt").c_str() : net_in.c_str(), device, &net));
+
+  std::mt19937_64 rng(seed + (unsigned long long) st.steps);
+  std::vector<int8_t> codes((size_t) std::max(batch, save_every) * 64);
+  std::vector<double> targets((size_t) std::max(batch, save_every));
+  auto draw = [&](long n) {                     // train.cpp:49: uniform draw with replacement
+    for (long i = 0; i < n; ++i) {
+      const cases::Case &c = cs[rng() % cs.size()];
+      std::memcpy(&codes[(size_t) i * 64], c.codes, 64);
+      targets[(size_t) i] = c.target;
+    }
+  };
+
+  long accepted = 0, decisions = 0, samples = 0, resets0 = st.resets, gen0 = st.generation;
+  double first_err = -1.0, last_err = -1.0;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (mode == "exact") {
+    std::vector<uint8_t> acc((size_t) save_every);
+    for (long done = 0; done < steps;) {
+      const long n = std::min(save_every, steps - done);
+      draw(n);
+      int resets = 0;
+      CK(cab_train_sequence(net, codes.data(), targets.data(), n, &st.lambda, seed + (unsigned long long) st.resets, acc.data(), &resets));
+      for (long i = 0; i < n; ++i) accepted += acc[(size_t) i];
+      decisions += n; samples += n; done += n;
+      st.steps += n; st.resets += resets;
+      if (n == save_every) CK(rotate(net, out_dir, st));
+    }
+  } else {
+    for (long s = 0; s < steps; ++s) {
+      draw(batch);
+      int acc = 0;
+      double e0 = 0.0, e1 = 0.0;
+      CK(cab_train_batch_host(net, codes.data(), targets.data(), batch, &st.lambda, 15.0, 1.1, &acc, &e0, &e1));
+      if (first_err < 0.0) first_err = e0;
+      last_err = acc ? e1 : e0;
+      accepted += acc; ++decisions; samples += batch; ++st.steps;
+      if (st.lambda < 1e-4 || st.lambda > 10.0) {          // train.cpp:54-57
+        st.lambda = 2.0;
+        CK(cab_dropout(net, 0.01, seed, (uint64_t) st.resets, nullptr));
+        ++st.resets;
+      }
+      if (st.steps % save_every == 0) CK(rotate(net, out_dir, st));
+    }
+  }
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  CK(rotate(net, out_dir, st));                 // NetworkStorage::flushStorage, network.cpp:366-370
+  long launches = 0;
+  cab_net_launch_count(net, &launches);
+  std::printf("{\"config\": \"trainer over packed case shards\", \"mode\": \"%s\", \"cases_in_shard\": %zu, \"steps\": %ld, \"batch\": %ld, "
+              "\"resumed\": %s, \"seconds\": %.3f, \"samples\": %ld, \"samples_per_s\": %.1f, \"accepted\": %ld, \"decisions\": %ld, "
+              "\"first_err\": %.9e, \"last_err\": %.9e, \"lambda\": %.17e, \"resets\": %ld, \"generations_written\": %ld, "
+              "\"total_steps\": %ld, \"gpu_launches\": %ld}\n",
+              mode.c_str(), cs.size(), steps, batch, resumed ? "true" : "false", secs, samples, samples / secs, accepted, decisions,
+              first_err, last_err, st.lambda, st.resets - resets0, st.generation - gen0, st.steps, launches);
+  cab_net_destroy(net);
+  return 0;
+}

@@ -356,3 +356,33 @@ extern "C" long ref_perft(const char *start_path, int depth) {
   game::Game *g = blank->clone();
   return ref_perft_rec(g, depth);
 }
+
+// ---- training-case rule ---------------------------------------------------------------
+double get_overall_result(double mcts_result, double game_result, double scale);  // make_cases.cpp:36 (external linkage)
+
+// The reference's two-stage target: SIMULATION_BOARD_SAVE_PROCEDURE (initialization.cpp:221-227, ratio 1.0 so the
+// board is always kept) maps the searched node's value to [-1,1]; get_overall_result mixes in the game result.
+extern "C" int ref_case_target(double node_value, int game_result, double *bounded_out, double *target_out) {
+  settings::PRINT_INITIALIZATION_DEBUG_INFORMATION = false;
+  init::updateTrainingParameters([] { return true; }, 20, 1.0);
+  std::vector<std::pair<game::Board *, double>> kept;
+  const int8_t empty[64] = {0};
+  game::Board *b = board_from_codes(empty);   // a parsed board: a bare Board(8,8) holds no piece objects to clone
+  settings::SIMULATION_BOARD_SAVE_PROCEDURE(kept, b, node_value);
+  delete b;
+  if (kept.size() != 1) return 1;
+  *bounded_out = kept[0].second;
+  *target_out = get_overall_result(kept[0].second, (double) game_result, 10.0);
+  delete kept[0].first;
+  return 0;
+}
+
+// Writes one training case with the reference's writer (Board::saveToFile + the target line of
+// network::save_training_case, make_cases.cpp:113-121), at an explicit path.
+extern "C" int ref_save_case(const int8_t *codes, double target, const char *path) {
+  game::Board *b = board_from_codes(codes);
+  if (b == nullptr) return 1;
+  b->saveToFile(path, [&](std::ostream &out) -> void { out << string::from_double(target) << std::endl; }, false);
+  delete b;
+  return 0;
+}
