@@ -82,6 +82,9 @@ _SIGS = {
     "cab_dp_init": [_vp, _vp, C.c_int, C.c_int],
     "cab_dp_shutdown": [_vp],
     "cab_grad_buffer": [_vp, C.POINTER(_vp), _lp],
+    "cab_train_batch_bf16_host": [_vp, _i8p, _f64p, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp],
+    "cab_train_batch_bf16_dev": [_vp, _vp, _vp, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp, _vp],
+    "cab_grad_bf16_dev": [_vp, _vp, _vp, C.c_long, _vp],
     "cab_measure_pipe_peak": [C.c_int, C.c_int, _dp],
     "cab_net_launch_count": [_vp, _lp],
 }
@@ -382,6 +385,15 @@ class Optimizer:
         t = np.ascontiguousarray(targets, dtype=np.float64)
         lam_c, acc, e0, e1 = C.c_double(lam), C.c_int(0), C.c_double(0), C.c_double(0)
         _ck(lib().cab_train_batch_host(network._h, c.reshape(-1), t, len(c), C.byref(lam_c), max_const, rate, C.byref(acc), C.byref(e0), C.byref(e1)))
+        return lam_c.value, bool(acc.value), e0.value, e1.value
+
+    @staticmethod
+    def train_batch_bf16(network, codes, targets, lam, max_const=15.0, rate=1.1):
+        """train_batch on the bf16 tcgen05 path (wide nets: hidden widths multiples of 256)."""
+        c = _as_codes(codes)
+        t = np.ascontiguousarray(targets, dtype=np.float64)
+        lam_c, acc, e0, e1 = C.c_double(lam), C.c_int(0), C.c_double(0), C.c_double(0)
+        _ck(lib().cab_train_batch_bf16_host(network._h, c.reshape(-1), t, len(c), C.byref(lam_c), max_const, rate, C.byref(acc), C.byref(e0), C.byref(e1)))
         return lam_c.value, bool(acc.value), e0.value, e1.value
 
 

@@ -106,6 +106,8 @@ struct cab_net {
   int8_t *d_tcodes = nullptr;
   double *d_ttargets = nullptr;
   double *d_tout = nullptr;
+  double *d_tout_tc = nullptr;  // outputs of the bf16 trainer's re-forward
+  long tout_cap = 0;
   long tbuf_cap = 0;
   double *d_scalars = nullptr; // small device scratch (lambda, flags ...)
   cudaStream_t train_stream = nullptr;

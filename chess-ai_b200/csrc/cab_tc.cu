@@ -10,7 +10,14 @@ namespace cab {
 
 struct TcState {
   std::vector<__nv_bfloat16 *> wt;  // per GEMM layer: Wt[N][K]
+  std::vector<__nv_bfloat16 *> wkn; // per GEMM layer l >= 1: W[K][N] (operand of the dX GEMM), packed on first training use
+  bool wkn_packed = false;
   float *w_last = nullptr;          // last layer (N = 1) in fp32
+  // training buffers (tc_train_prepare): saved activations a_l and psi_l, row-major [B][width] and transposed [width][ld]
+  std::vector<__nv_bfloat16 *> a_rm, a_t, p_rm, p_t;
+  float *psi_out = nullptr;
+  double *y = nullptr;
+  long train_cap = 0, ld = 0;
   __nv_bfloat16 *act[2] = {nullptr, nullptr};
   double *d_out = nullptr;
   int8_t *d_codes = nullptr;
@@ -35,10 +42,11 @@ static int load_encode() {
   return CAB_OK;
 }
 
-// row-major bf16 matrix [rows][cols] (cols contiguous) -> tiled map with box {64 cols, box_rows}, 128-byte swizzle
-static int make_map(CUtensorMap *m, const void *ptr, long rows, long cols, int box_rows) {
+// row-major bf16 matrix [rows][cols] (cols contiguous, row stride ld elements; 0 = cols) -> tiled map with box
+// {64 cols, box_rows}, 128-byte swizzle; reads past rows / cols are zero-filled
+static int make_map(CUtensorMap *m, const void *ptr, long rows, long cols, int box_rows, long ld = 0) {
   const cuuint64_t gdim[2] = {(cuuint64_t) cols, (cuuint64_t) rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t) cols * 2};
+  const cuuint64_t gstride[1] = {(cuuint64_t) (ld ? ld : cols) * 2};
   const cuuint32_t box[2] = {(cuuint32_t) tc::BK, (cuuint32_t) box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
@@ -60,6 +68,10 @@ void tc_free(cab_net *net) {
   TcState *s = static_cast<TcState *>(net->tc);
   if (!s) return;
   for (auto *p : s->wt) cudaFree(p);
+  for (auto *p : s->wkn) cudaFree(p);
+  for (auto *v : {&s->a_rm, &s->a_t, &s->p_rm, &s->p_t})
+    for (auto *p : *v) cudaFree(p);
+  cudaFree(s->psi_out); cudaFree(s->y);
   cudaFree(s->w_last); cudaFree(s->act[0]); cudaFree(s->act[1]); cudaFree(s->d_out); cudaFree(s->d_codes);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -86,7 +98,9 @@ static int tc_prepare(cab_net *net, long n, cudaStream_t stream) {
     }
     CAB_CUDA(cudaMalloc(&s->w_last, (size_t) net->dims[L - 2] * sizeof(float)));
     CAB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CAB_CUDA(cudaFuncSetAttribute(tc::tc_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc::kSmemTc));
+    CAB_CUDA(cudaFuncSetAttribute(tc::tc_gemm_bf16_kernel<tc::kEpiAct>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc::kSmemTc));
+    CAB_CUDA(cudaFuncSetAttribute(tc::tc_gemm_bf16_kernel<tc::kEpiDeriv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc::kSmemTc));
+    CAB_CUDA(cudaFuncSetAttribute(tc::tc_gemm_bf16_kernel<tc::kEpiGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc::kSmemTc));
   }
   if (stream == nullptr) stream = s->stream;  // host entry point: everything on the state's own stream
   if (!s->packed || net->tc_dirty) {
@@ -100,6 +114,7 @@ static int tc_prepare(cab_net *net, long n, cudaStream_t stream) {
     CAB_CUDA(cudaGetLastError());
     CAB_CUDA(cudaStreamSynchronize(stream));  // rare (weights changed): later launches may sit on another stream
     s->packed = true;
+    s->wkn_packed = false;
     net->tc_dirty = false;
   }
   if (n > s->cap) {
@@ -114,32 +129,153 @@ static int tc_prepare(cab_net *net, long n, cudaStream_t stream) {
   return CAB_OK;
 }
 
-static int tc_forward(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream) {
-  int rc = tc_prepare(net, n, stream);
-  if (rc != CAB_OK) return rc;
-  TcState *s = static_cast<TcState *>(net->tc);
-  const int L = (int) net->dims.size();
-  tc::codes_to_bf16_kernel<<<(int) std::min<long>((n * 64 + 255) / 256, 148L * 16), 256, 0, stream>>>(d_codes, n * 64, s->act[0]);
-  net->launches++;
-  int cur = 0;
-  for (int l = 0; l + 2 < L; ++l) {
-    const int K = net->dims[l], N = net->dims[l + 1];
-    CUtensorMap mx, mw;
-    if ((rc = make_map(&mx, s->act[cur], n, K, tc::BM)) != CAB_OK) return rc;
-    if ((rc = make_map(&mw, s->wt[l], N, K, tc::BN)) != CAB_OK) return rc;
-    tc::TcGemmArgs a{(int) n, N, K, s->act[1 - cur], 1};
-    const int tiles = (int) ((n + tc::BM - 1) / tc::BM) * (N / tc::BN);
-    tc::tc_gemm_bf16_kernel<<<std::min(tiles, net->sm_count), tc::kThreadsTc, tc::kSmemTc, stream>>>(mx, mw, a);
-    net->launches++;
-    CAB_CUDA(cudaGetLastError());
-    cur = 1 - cur;
-  }
-  const int K = net->dims[L - 2];
-  tc::gemv_out_kernel<<<(int) ((n * 32 + 255) / 256), 256, 0, stream>>>(s->act[cur], s->w_last, n, K, d_out);
+static int launch_gemm(cab_net *net, int epi, const CUtensorMap &ma, const CUtensorMap &mb, const tc::TcGemmArgs &a, cudaStream_t stream) {
+  const int tiles = ((a.M + tc::BM - 1) / tc::BM) * (a.N / tc::BN);
+  const int grid = std::min(tiles * std::max(1, a.split_k), net->sm_count);
+  if (epi == tc::kEpiAct) tc::tc_gemm_bf16_kernel<tc::kEpiAct><<<grid, tc::kThreadsTc, tc::kSmemTc, stream>>>(ma, mb, a);
+  else if (epi == tc::kEpiDeriv) tc::tc_gemm_bf16_kernel<tc::kEpiDeriv><<<grid, tc::kThreadsTc, tc::kSmemTc, stream>>>(ma, mb, a);
+  else tc::tc_gemm_bf16_kernel<tc::kEpiGrad><<<grid, tc::kThreadsTc, tc::kSmemTc, stream>>>(ma, mb, a);
   net->launches++;
   CAB_CUDA(cudaGetLastError());
   return CAB_OK;
 }
+
+// save = false: ping-pong buffers (evaluation). save = true: every layer's activation is kept row-major (a_rm) and,
+// where the dW GEMM will contract over boards, transposed (a_t) — propagate_for_training, network.cpp:139-153.
+static int tc_forward(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream, bool save = false) {
+  int rc = tc_prepare(net, n, stream);
+  if (rc != CAB_OK) return rc;
+  TcState *s = static_cast<TcState *>(net->tc);
+  const int L = (int) net->dims.size();
+  __nv_bfloat16 *x0 = save ? s->a_rm[0] : s->act[0];
+  tc::codes_to_bf16_kernel<<<(int) std::min<long>((n * 64 + 255) / 256, 148L * 16), 256, 0, stream>>>(d_codes, n * 64, x0);
+  net->launches++;
+  if (save) {
+    tc::codes_to_bf16_t_kernel<<<(int) std::min<long>((n * 64 + 255) / 256, 148L * 16), 256, 0, stream>>>(d_codes, n, s->ld, s->a_t[0]);
+    net->launches++;
+  }
+  int cur = 0;
+  const __nv_bfloat16 *in = x0;
+  for (int l = 0; l + 2 < L; ++l) {
+    const int K = net->dims[l], N = net->dims[l + 1];
+    CUtensorMap mx, mw;
+    if ((rc = make_map(&mx, in, n, K, tc::BM)) != CAB_OK) return rc;
+    if ((rc = make_map(&mw, s->wt[l], N, K, tc::BN)) != CAB_OK) return rc;
+    tc::TcGemmArgs a{};
+    a.M = (int) n; a.N = N; a.K = K;
+    a.Y = save ? s->a_rm[l + 1] : s->act[1 - cur];
+    a.Yt = (save && l + 3 < L) ? s->a_t[l + 1] : nullptr;     // a_{L-2} feeds only the last layer's GEMV
+    a.ldt = s->ld;
+    a.split_k = 1;
+    a.apply_act = 1;
+    if ((rc = launch_gemm(net, tc::kEpiAct, mx, mw, a, stream)) != CAB_OK) return rc;
+    in = a.Y;
+    cur = 1 - cur;
+  }
+  const int K = net->dims[L - 2];
+  tc::gemv_out_kernel<<<(int) ((n * 32 + 255) / 256), 256, 0, stream>>>(in, s->w_last, n, K, d_out);
+  net->launches++;
+  CAB_CUDA(cudaGetLastError());
+  return CAB_OK;
+}
+
+static int tc_train_prepare(cab_net *net, long n, cudaStream_t stream) {
+  int rc = tc_prepare(net, n, stream);
+  if (rc != CAB_OK) return rc;
+  TcState *s = static_cast<TcState *>(net->tc);
+  const int L = (int) net->dims.size();
+  if (s->wkn.empty()) {
+    s->wkn.assign(L - 2, nullptr);
+    for (int l = 1; l + 2 < L; ++l) CAB_CUDA(cudaMalloc(&s->wkn[l], (size_t) net->dims[l] * net->dims[l + 1] * 2));
+  }
+  if (!s->wkn_packed) {
+    for (int l = 1; l + 2 < L; ++l) {
+      const long total = (long) net->dims[l] * net->dims[l + 1];
+      tc::pack_w_bf16_kernel<<<(int) std::min<long>((total + 255) / 256, 148L * 16), 256, 0, stream>>>(net->d_w + net->woff[l], total, s->wkn[l]);
+      net->launches++;
+    }
+    CAB_CUDA(cudaGetLastError());
+    s->wkn_packed = true;
+  }
+  if (n > s->train_cap) {
+    for (auto *v : {&s->a_rm, &s->a_t, &s->p_rm, &s->p_t}) {
+      for (auto *p : *v) cudaFree(p);
+      v->assign(L - 1, nullptr);
+    }
+    cudaFree(s->psi_out); cudaFree(s->y);
+    const long ld = (n + tc::BM - 1) / tc::BM * tc::BM;
+    for (int l = 0; l + 1 < L; ++l) {
+      const size_t bytes = (size_t) ld * net->dims[l] * 2;
+      CAB_CUDA(cudaMalloc(&s->a_rm[l], bytes));
+      if (l + 2 < L) { CAB_CUDA(cudaMalloc(&s->a_t[l], bytes)); CAB_CUDA(cudaMemset(s->a_t[l], 0, bytes)); }
+      if (l >= 1) {
+        CAB_CUDA(cudaMalloc(&s->p_rm[l], bytes));
+        CAB_CUDA(cudaMalloc(&s->p_t[l], bytes));
+        CAB_CUDA(cudaMemset(s->p_t[l], 0, bytes));
+      }
+    }
+    CAB_CUDA(cudaMalloc(&s->psi_out, ld * sizeof(float)));
+    CAB_CUDA(cudaMalloc(&s->y, ld * sizeof(double)));
+    CAB_CUDA(cudaDeviceSynchronize());   // the memsets ran on the legacy stream
+    s->train_cap = n;
+    s->ld = ld;
+  }
+  return CAB_OK;
+}
+
+// Forward with saved activations + backward, leaving sum_b dW in grad[0 .. nw) (fp64, the reference's n,i,j order) and
+// sum_b E in grad[nw]. The caller zeroed grad. Mirrors K2 -> mlp_backward_kernel -> grad_kernel of the fp64 path.
+int tc_grad(cab_net *net, const int8_t *d_codes, const double *d_targets, long n, double *d_grad, cudaStream_t stream) {
+  int rc = tc_train_prepare(net, n, stream);
+  if (rc != CAB_OK) return rc;
+  TcState *s = static_cast<TcState *>(net->tc);
+  const int L = (int) net->dims.size();
+  if ((rc = tc_forward(net, d_codes, n, s->y, stream, /*save=*/true)) != CAB_OK) return rc;
+  // output neuron and the last (N = 1) layer
+  const int KL = net->dims[L - 2];
+  tc::out_delta_kernel<<<(int) std::min<long>((n + 255) / 256, 148L * 4), 256, 0, stream>>>(s->y, d_targets, n, s->psi_out, d_grad + net->n_weights);
+  const long slice = std::max<long>(64, (n + 63) / 64);
+  tc::gemv_t_kernel<<<dim3((KL / 2 + 255) / 256, (unsigned) ((n + slice - 1) / slice)), 256, 0, stream>>>(
+      s->a_rm[L - 2], s->psi_out, n, KL, slice, d_grad + net->woff[L - 2]);
+  tc::psi_last_kernel<<<dim3((unsigned) ((n + 63) / 64), KL / 64), 256, 0, stream>>>(s->a_rm[L - 2], s->w_last, s->psi_out, n, KL,
+                                                                                    s->p_rm[L - 2], s->p_t[L - 2], s->ld);
+  net->launches += 3;
+  CAB_CUDA(cudaGetLastError());
+  for (int l = L - 3; l >= 0; --l) {
+    const int K = net->dims[l], N = net->dims[l + 1];
+    {  // dW_l[K][N] = a_l^T psi_{l+1}: contraction over boards, both operands read from their transposed copies
+      CUtensorMap ma, mb;
+      if ((rc = make_map(&ma, s->a_t[l], K, n, tc::BM, s->ld)) != CAB_OK) return rc;
+      if ((rc = make_map(&mb, s->p_t[l + 1], N, n, tc::BN, s->ld)) != CAB_OK) return rc;
+      tc::TcGemmArgs a{};
+      a.M = K; a.N = N; a.K = (int) n;
+      a.G = d_grad + net->woff[l];
+      const int tiles = ((K + tc::BM - 1) / tc::BM) * (N / tc::BN);
+      const int kblocks = (int) ((n + tc::BK - 1) / tc::BK);
+      // narrow layers (the 64-wide input) have too few output tiles to fill the chip: split the board dimension
+      a.split_k = tiles * 2 > net->sm_count ? 1 : std::max(1, std::min(kblocks / 8, net->sm_count / tiles));
+      if ((rc = launch_gemm(net, tc::kEpiGrad, ma, mb, a, stream)) != CAB_OK) return rc;
+    }
+    if (l >= 1) {  // psi_l = (psi_{l+1} W_l^T) * f'(a_l); the input layer needs no psi (network.cpp:248: L stops at 0)
+      CUtensorMap ma, mb;
+      if ((rc = make_map(&ma, s->p_rm[l + 1], n, N, tc::BM)) != CAB_OK) return rc;
+      if ((rc = make_map(&mb, s->wkn[l], K, N, tc::BN)) != CAB_OK) return rc;
+      tc::TcGemmArgs a{};
+      a.M = (int) n; a.N = K; a.K = N;
+      a.Y = s->p_rm[l]; a.Yt = s->p_t[l]; a.ldt = s->ld;
+      a.aux = s->a_rm[l];
+      a.split_k = 1;
+      if ((rc = launch_gemm(net, tc::kEpiDeriv, ma, mb, a, stream)) != CAB_OK) return rc;
+    }
+  }
+  return CAB_OK;
+}
+
+int tc_forward_out(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream) {
+  return tc_forward(net, d_codes, n, d_out, stream);
+}
+
+bool tc_fits(const cab_net *net) { return tc_supported(net); }
 
 }  // namespace cab
 

@@ -247,27 +247,48 @@ static int fan_out(cab_net *net, cudaStream_t stream, long n, F &&piece) {
   return CAB_OK;
 }
 
+// bf16 tensor-core providers (cab_tc.cu): gradient and plain forward for nets whose hidden widths fit the GEMM tiles
+int tc_grad(cab_net *net, const int8_t *d_codes, const double *d_targets, long n, double *d_grad, cudaStream_t stream);
+int tc_forward_out(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream);
+bool tc_fits(const cab_net *net);
+
+static int ensure_tout(cab_net *net, long n) {   // bf16 mode: only the output buffer of the re-forward
+  if (n > net->tout_cap) {
+    cudaFree(net->d_tout_tc);
+    net->d_tout_tc = nullptr;
+    CAB_CUDA(cudaMalloc(&net->d_tout_tc, n * sizeof(double)));
+    net->tout_cap = n;
+  }
+  return CAB_OK;
+}
+
 static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d_targets, long n, double *lambda,
                             double max_const, double rate, int *accepted, double *err, double *new_err,
-                            cudaStream_t stream) {
-  if (!net->fp64_ok) { set_error("layer too wide for the fp64 training kernels"); return CAB_EINVAL; }
+                            cudaStream_t stream, bool bf16 = false) {
+  if (!bf16 && !net->fp64_ok) { set_error("layer too wide for the fp64 training kernels"); return CAB_EINVAL; }
+  if (bf16 && !tc_fits(net)) { set_error("bf16 tcgen05 training needs hidden widths that are multiples of 256"); return CAB_EINVAL; }
   int rc = ensure_train_state(net);
   if (rc != CAB_OK) return rc;
-  if ((rc = ensure_batch_buffers(net, n)) != CAB_OK) return rc;
+  if ((rc = bf16 ? ensure_tout(net, n) : ensure_batch_buffers(net, n)) != CAB_OK) return rc;
+  double *d_tout = bf16 ? net->d_tout_tc : net->d_tout;
   const long nw = net->n_weights;
-  {
+  if (!bf16) {
     std::lock_guard<std::mutex> lk(net->mu);
     if ((rc = ensure_packed(net, stream)) != CAB_OK) return rc;
   }
   CAB_CUDA(cudaMemsetAsync(net->d_grad, 0, (nw + 4) * sizeof(double), stream));
   set_scalar_kernel<<<1, 1, 0, stream>>>(net->d_grad + nw + 2, (double) n);
-  // forward with saved activations (propagate_for_training), backward, gradient
-  rc = fan_out(net, stream, n, [&](long b0, long nb, cudaStream_t s) {
-    int r = launch_forward(net, d_codes + b0 * 64, nb, net->d_tout + b0, net->d_acts + b0 * 8, net->train_cap * 8, s);
-    return r != CAB_OK ? r : launch_backward(net, d_targets, b0, nb, s);   // same stream: backward follows its forward
-  });
-  if (rc != CAB_OK) return rc;
-  if ((rc = launch_grad(net, n, stream)) != CAB_OK) return rc;
+  if (bf16) {
+    if ((rc = tc_grad(net, d_codes, d_targets, n, net->d_grad, stream)) != CAB_OK) return rc;
+  } else {
+    // forward with saved activations (propagate_for_training), backward, gradient
+    rc = fan_out(net, stream, n, [&](long b0, long nb, cudaStream_t s) {
+      int r = launch_forward(net, d_codes + b0 * 64, nb, net->d_tout + b0, net->d_acts + b0 * 8, net->train_cap * 8, s);
+      return r != CAB_OK ? r : launch_backward(net, d_targets, b0, nb, s);   // same stream: backward follows its forward
+    });
+    if (rc != CAB_OK) return rc;
+    if ((rc = launch_grad(net, n, stream)) != CAB_OK) return rc;
+  }
   if (net->nccl_comm != nullptr) {  // sum of (G, E, -, count) over ranks
     int nrc = g_nccl.AllReduce(net->d_grad, net->d_grad, (size_t) nw + 4, kNcclDouble, kNcclSum, net->nccl_comm, stream);
     if (nrc != 0) return nccl_fail(nrc, "ncclAllReduce(grad)");
@@ -275,17 +296,21 @@ static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d
   apply_update_kernel<<<(int) std::min<long>((nw + 255) / 256, 148L * 8), 256, 0, stream>>>(net->d_w, net->d_dw, net->d_grad, nw, *lambda);
   net->launches += 2;
   net->pack_dirty = net->tc_dirty = true;
-  {
-    std::lock_guard<std::mutex> lk(net->mu);
-    if ((rc = ensure_packed(net, stream)) != CAB_OK) return rc;
-  }
   // re-forward (network.cpp:265) and E'
-  rc = fan_out(net, stream, n, [&](long b0, long nb, cudaStream_t s) {
-    return launch_forward(net, d_codes + b0 * 64, nb, net->d_tout + b0, nullptr, 0, s);
-  });
-  if (rc != CAB_OK) return rc;
+  if (bf16) {
+    if ((rc = tc_forward_out(net, d_codes, n, d_tout, stream)) != CAB_OK) return rc;
+  } else {
+    {
+      std::lock_guard<std::mutex> lk(net->mu);
+      if ((rc = ensure_packed(net, stream)) != CAB_OK) return rc;
+    }
+    rc = fan_out(net, stream, n, [&](long b0, long nb, cudaStream_t s) {
+      return launch_forward(net, d_codes + b0 * 64, nb, net->d_tout + b0, nullptr, 0, s);
+    });
+    if (rc != CAB_OK) return rc;
+  }
   CAB_CUDA(cudaMemsetAsync(net->d_scalars, 0, 2 * sizeof(double), stream));
-  batch_error_kernel<<<(int) std::min<long>((n + 255) / 256, 148L * 4), 256, 0, stream>>>(net->d_tout, d_targets, n, net->d_scalars);
+  batch_error_kernel<<<(int) std::min<long>((n + 255) / 256, 148L * 4), 256, 0, stream>>>(d_tout, d_targets, n, net->d_scalars);
   net->launches++;
   if (net->nccl_comm != nullptr) {
     int nrc = g_nccl.AllReduce(net->d_scalars, net->d_scalars, 1, kNcclDouble, kNcclSum, net->nccl_comm, stream);
@@ -430,6 +455,44 @@ int cab_train_batch_host(cab_net *net, const int8_t *codes, const double *target
   CAB_CUDA(cudaMemcpyAsync(net->d_tcodes, codes, n * 64, cudaMemcpyHostToDevice, s));
   CAB_CUDA(cudaMemcpyAsync(net->d_ttargets, targets, n * sizeof(double), cudaMemcpyHostToDevice, s));
   return train_batch_impl(net, net->d_tcodes, net->d_ttargets, n, lambda, max_const, rate, accepted, err, new_err, s);
+}
+
+int cab_train_batch_bf16_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n, double *lambda,
+                             double max_const, double rate, int *accepted, double *err, double *new_err, void *stream) {
+  if (!net || !lambda || n <= 0 || !codes_dev || !targets_dev) { set_error("bad argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  return train_batch_impl(net, codes_dev, targets_dev, n, lambda, max_const, rate, accepted, err, new_err,
+                          stream ? (cudaStream_t) stream : net->train_stream, /*bf16=*/true);
+}
+
+int cab_train_batch_bf16_host(cab_net *net, const int8_t *codes, const double *targets, long n, double *lambda,
+                              double max_const, double rate, int *accepted, double *err, double *new_err) {
+  if (!net || !lambda || n <= 0 || !codes || !targets) { set_error("bad argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  if ((rc = ensure_host_staging(net, n)) != CAB_OK) return rc;
+  cudaStream_t s = net->train_stream;
+  CAB_CUDA(cudaMemcpyAsync(net->d_tcodes, codes, n * 64, cudaMemcpyHostToDevice, s));
+  CAB_CUDA(cudaMemcpyAsync(net->d_ttargets, targets, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  return train_batch_impl(net, net->d_tcodes, net->d_ttargets, n, lambda, max_const, rate, accepted, err, new_err, s, /*bf16=*/true);
+}
+
+// Forward (activations saved) + backward only: leaves sum_b dW (fp64, n,i,j order) in cab_grad_buffer()[0 .. nw) and
+// sum_b E, -, count behind it. The timed unit of BASELINE.json configs[4] ("bf16 tcgen05 fwd+bwd").
+int cab_grad_bf16_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n, void *stream) {
+  if (!net || n <= 0 || !codes_dev || !targets_dev) { set_error("bad argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  if (!tc_fits(net)) { set_error("bf16 tcgen05 training needs hidden widths that are multiples of 256"); return CAB_EINVAL; }
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  cudaStream_t s = stream ? (cudaStream_t) stream : net->train_stream;
+  CAB_CUDA(cudaMemsetAsync(net->d_grad, 0, (net->n_weights + 4) * sizeof(double), s));
+  set_scalar_kernel<<<1, 1, 0, s>>>(net->d_grad + net->n_weights + 2, (double) n);
+  net->launches++;
+  return tc_grad(net, codes_dev, targets_dev, n, net->d_grad, s);
 }
 
 int cab_dp_unique_id(void *id128_out) {

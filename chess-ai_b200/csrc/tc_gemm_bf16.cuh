@@ -86,12 +86,27 @@ __device__ __forceinline__ float act_f32(float x) {
   return 4.0f * t;
 }
 
+// Epilogue flavours of the one GEMM kernel  D[M][N] = A[M][K] * Bt[N][K]^T  (both operands contraction-contiguous):
+//   kEpiAct    forward layer:   Y = f(D)                        bf16 row-major (+ optional transposed copy Yt[N][ldt])
+//   kEpiDeriv  backward dX:     Y = D * f'(a), a = aux[M][N]    bf16 row-major (+ transposed copy): psi of the layer
+//                               below (network.cpp:250-257: omega accumulated through W, times df of the saved theta;
+//                               f'(theta) = 1 - (a/4)^2 in closed form from the saved activation)
+//   kEpiGrad   backward dW:     G[M][N] (+)= D                  fp64, row-major = the reference's [in][out] weight order
+//                               (network.cpp:258: dW = psi * a summed over the batch); split-K work items add with red.f64
+enum { kEpiAct = 0, kEpiDeriv = 1, kEpiGrad = 2 };
+
 struct TcGemmArgs {
   int M, N, K;
-  __nv_bfloat16 *Y;   // [M][N]
-  int apply_act;
+  __nv_bfloat16 *Y;          // [M][N]                      (kEpiAct / kEpiDeriv)
+  __nv_bfloat16 *Yt;         // [N][ldt] or nullptr         (kEpiAct / kEpiDeriv)
+  long ldt;
+  const __nv_bfloat16 *aux;  // [M][N] saved activation     (kEpiDeriv)
+  double *G;                 // [M][N]                      (kEpiGrad)
+  int split_k;               // work items per output tile  (kEpiGrad; 1 elsewhere)
+  int apply_act;             // kEpiAct: 0 = plain product
 };
 
+template <int EPI>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const TcGemmArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -106,7 +121,10 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blocks_n = args.N / BN, n_blocks_m = (args.M + BM - 1) / BM;
-  const int n_tiles = n_blocks_m * n_blocks_n, n_kblocks = args.K / BK;
+  const int n_kblocks = (args.K + BK - 1) / BK;            // a ragged tail is zero-filled by TMA
+  const int kb_per_item = (n_kblocks + args.split_k - 1) / args.split_k;
+  const int n_splits = (n_kblocks + kb_per_item - 1) / kb_per_item;
+  const int n_items = n_blocks_m * n_blocks_n * n_splits;  // item = (tile, k-split), splits of a tile adjacent
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStagesTc; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -126,9 +144,11 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // ------------------------------------------- TMA producer -------------------------------------------
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item / n_splits, split = item % n_splits;
         const int mb = tile / n_blocks_n, nb = tile % n_blocks_n;
-        for (int kb = 0; kb < n_kblocks; ++kb) {
+        const int kb0 = split * kb_per_item, kb1 = min(kb0 + kb_per_item, n_kblocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], kBytesA + kBytesB);
           tma_load_2d(smem_a + (size_t) s * kBytesA, &tmap_x, kb * BK, mb * BM, &full[s]);
@@ -140,11 +160,13 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------- MMA issuer ---------------------------------------------
     uint32_t s = 0, ph = 0, as = 0, aph = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int split = item % n_splits;
+      const int kb0 = split * kb_per_item, kb1 = min(kb0 + kb_per_item, n_kblocks);
       mbar_wait(&tmem_empty[as], aph ^ 1);          // the epilogue drained this accumulator
       tmem_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t) as * BN;
-      for (int kb = 0; kb < n_kblocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[s], ph);                    // TMA bytes landed
         tmem_fence_after();
         if (lane == 0) {
@@ -152,9 +174,9 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + (size_t) s * kBytesB));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)     // advance 32 B inside the swizzle atom: +2 in the >>4 address field
-            umma_f16(tmem_d, a_desc + (uint64_t) (k * 2), b_desc + (uint64_t) (k * 2), kIdesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_d, a_desc + (uint64_t) (k * 2), b_desc + (uint64_t) (k * 2), kIdesc, (kb != kb0 || k != 0) ? 1u : 0u);
           umma_commit(&empty[s]);                   // frees the smem stage when these MMAs retire
-          if (kb == n_kblocks - 1) umma_commit(&tmem_full[as]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
         }
         __syncwarp();
         if (++s == kStagesTc) { s = 0; ph ^= 1; }
@@ -165,28 +187,84 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // ------------------------------------------- epilogue -----------------------------------------------
     const int q = warp & 3;                          // TMEM lane quarter this warp may read
     uint32_t as = 0, aph = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int tile = item / n_splits;
       const int mb = tile / n_blocks_n, nb = tile % n_blocks_n;
       mbar_wait(&tmem_full[as], aph);
       tmem_fence_after();
       const int row = mb * BM + q * 32 + lane;
-      __nv_bfloat16 *yrow = args.Y + (size_t) row * args.N + (size_t) nb * BN;
+      const size_t row_off = (size_t) row * args.N + (size_t) nb * BN;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (as * BN + c), r);
-        uint32_t packed[16];
+        if (EPI == kEpiGrad) {
+          if (row < args.M) {
+            double *g = args.G + row_off + c;
+            if (n_splits == 1) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float v0 = __uint_as_float(r[2 * i]), v1 = __uint_as_float(r[2 * i + 1]);
-          if (args.apply_act) { v0 = act_f32(v0); v1 = act_f32(v1); }
-          __nv_bfloat162 b = __floats2bfloat162_rn(v0, v1);
-          packed[i] = *reinterpret_cast<uint32_t *>(&b);
-        }
-        if (row < args.M) {
-          uint4 *dst = reinterpret_cast<uint4 *>(yrow + c);
+              for (int i = 0; i < 32; i += 2)
+                *reinterpret_cast<double2 *>(g + i) = make_double2((double) __uint_as_float(r[i]), (double) __uint_as_float(r[i + 1]));
+            } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+              for (int i = 0; i < 32; ++i)
+                asm volatile("red.global.add.f64 [%0], %1;" ::"l"(g + i), "d"((double) __uint_as_float(r[i])) : "memory");
+            }
+          }
+        } else {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (EPI == kEpiAct) {
+            if (args.apply_act) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = act_f32(v[i]);
+            }
+          } else {
+            uint4 a4[4] = {};
+            if (row < args.M) {
+              const uint4 *ap = reinterpret_cast<const uint4 *>(args.aux + row_off + c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) a4[i] = __ldg(ap + i);
+            }
+            const __nv_bfloat162 *ab = reinterpret_cast<const __nv_bfloat162 *>(a4);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 a = __bfloat1622float2(ab[i]);
+              v[2 * i] *= 1.0f - 0.0625f * a.x * a.x;
+              v[2 * i + 1] *= 1.0f - 0.0625f * a.y * a.y;
+            }
+          }
+          if (row >= args.M) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;  // pad rows of the transposed copy stay zero
+          }
+          if (row < args.M) {
+            uint4 *dst = reinterpret_cast<uint4 *>(args.Y + row_off + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t *>(&b);
+              }
+              dst[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          if (args.Yt != nullptr) {
+            // transposed copy: lanes are consecutive rows; lane pairs swap so that each lane stores two rows of one
+            // column as one 4-byte word -> every column receives 64 contiguous bytes from the warp
+            __nv_bfloat16 *tcol = args.Yt + (size_t) (nb * BN + c) * args.ldt + (row & ~1);
+            const bool odd = lane & 1;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float send = odd ? v[i] : v[i + 1];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+              const __nv_bfloat162 b = odd ? __floats2bfloat162_rn(recv, v[i + 1]) : __floats2bfloat162_rn(v[i], recv);
+              *reinterpret_cast<__nv_bfloat162 *>(tcol + (size_t) (i + (odd ? 1 : 0)) * args.ldt) = b;
+            }
+          }
         }
       }
       tmem_fence_before();
@@ -237,6 +315,98 @@ __global__ void __launch_bounds__(256) pack_wt_bf16_kernel(const double *__restr
 }
 __global__ void __launch_bounds__(256) pack_last_f32_kernel(const double *__restrict__ w, int K, float *__restrict__ out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) out[i] = (float) w[i];
+}
+
+
+// ---- training-side helpers of the bf16 path (all HBM-trivial next to the GEMMs) ---------------------------------
+// transposed copy of the inputs: xt[j][b] = k * 0.4 (row stride ldt, pad columns zeroed by the caller's memset)
+__global__ void __launch_bounds__(256) codes_to_bf16_t_kernel(const int8_t *__restrict__ codes, long n_boards, long ldt,
+                                                               __nv_bfloat16 *__restrict__ xt) {
+  const long total = n_boards * 64;
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < total; i += (long) gridDim.x * blockDim.x) {
+    const long j = i / n_boards, b = i % n_boards;
+    xt[j * ldt + b] = __float2bfloat16_rn((float) codes[b * 64 + j] * 0.4f);
+  }
+}
+
+// W[K][N] fp64 -> bf16, same layout: the B operand of the dX GEMM (contraction over N)
+__global__ void __launch_bounds__(256) pack_w_bf16_kernel(const double *__restrict__ w, long total, __nv_bfloat16 *__restrict__ out) {
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < total; i += (long) gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn((float) w[i]);
+}
+
+// output neuron: omega = T - y, E += omega^2 / 2, psi_out = omega * f'(theta_out)   (network.cpp:242-243, 250)
+__global__ void __launch_bounds__(256) out_delta_kernel(const double *__restrict__ y, const double *__restrict__ t, long n,
+                                                         float *__restrict__ psi_out, double *__restrict__ err_sum) {
+  double e = 0.0;
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+    const double yv = y[i], om = t[i] - yv;
+    e += om * om / 2.0;
+    psi_out[i] = (float) (om * (1.0 - yv * yv / 16.0));
+  }
+  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+  if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(err_sum, e);
+}
+
+// dW of the last layer (N = 1): g[k] += sum_b psi_out[b] * a[b][k]. Thread = two columns, blockIdx.y = board slice.
+__global__ void __launch_bounds__(256) gemv_t_kernel(const __nv_bfloat16 *__restrict__ a, const float *__restrict__ psi_out, long n_boards,
+                                                      int K, long slice, double *__restrict__ g) {
+  const int k2 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k2 >= K / 2) return;
+  const long b0 = blockIdx.y * slice, b1 = min(b0 + slice, n_boards);
+  float s0 = 0.f, s1 = 0.f;
+  for (long b = b0; b < b1; ++b) {
+    const float2 v = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162 *>(a + b * K)[k2]);
+    const float p = psi_out[b];
+    s0 = fmaf(p, v.x, s0);
+    s1 = fmaf(p, v.y, s1);
+  }
+  atomicAdd(g + 2 * k2, (double) s0);
+  atomicAdd(g + 2 * k2 + 1, (double) s1);
+}
+
+// psi of the last hidden layer: psi[b][k] = psi_out[b] * w_last[k] * f'(a[b][k]), row-major and transposed.
+// One CTA = a 64-board x 64-feature tile, transposed through shared memory.
+__global__ void __launch_bounds__(256) psi_last_kernel(const __nv_bfloat16 *__restrict__ a, const float *__restrict__ w_last,
+                                                        const float *__restrict__ psi_out, long n_boards, int K,
+                                                        __nv_bfloat16 *__restrict__ psi, __nv_bfloat16 *__restrict__ psi_t, long ldt) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64][72];
+  const long b0 = blockIdx.x * 64L;
+  const int k0 = blockIdx.y * 64;
+  {
+    const int r = threadIdx.x >> 2, cq = (threadIdx.x & 3) * 16;
+    const long b = b0 + r;
+    uint4 raw[2] = {};
+    float po = 0.f;
+    if (b < n_boards) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(a + b * K + k0 + cq);
+      raw[0] = __ldg(src); raw[1] = __ldg(src + 1);
+      po = psi_out[b];
+    }
+    const __nv_bfloat162 *ab = reinterpret_cast<const __nv_bfloat162 *>(raw);
+    __nv_bfloat162 out[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 v = __bfloat1622float2(ab[i]);
+      const float p0 = po * w_last[k0 + cq + 2 * i] * (1.0f - 0.0625f * v.x * v.x);
+      const float p1 = po * w_last[k0 + cq + 2 * i + 1] * (1.0f - 0.0625f * v.y * v.y);
+      out[i] = __floats2bfloat162_rn(p0, p1);
+      tile[cq + 2 * i][r] = out[i].x;
+      tile[cq + 2 * i + 1][r] = out[i].y;
+    }
+    if (b < n_boards) {
+      uint4 *dst = reinterpret_cast<uint4 *>(psi + b * K + k0 + cq);
+      dst[0] = reinterpret_cast<const uint4 *>(out)[0];
+      dst[1] = reinterpret_cast<const uint4 *>(out)[1];
+    }
+  }
+  __syncthreads();
+  {
+    const int kk = threadIdx.x >> 2, bq = (threadIdx.x & 3) * 16;
+    uint4 *dst = reinterpret_cast<uint4 *>(psi_t + (long) (k0 + kk) * ldt + b0 + bq);   // pad boards carry zeros
+    dst[0] = *reinterpret_cast<const uint4 *>(&tile[kk][bq]);
+    dst[1] = *reinterpret_cast<const uint4 *>(&tile[kk][bq + 8]);
+  }
 }
 
 }  // namespace tc

@@ -137,6 +137,17 @@ CAB_API int cab_train_batch_host(cab_net *net, const int8_t *codes_host, const d
 CAB_API int cab_train_batch_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases,
                         double *lambda, double max_const, double rate, int *accepted, double *err, double *new_err,
                         void *stream);
+/* The same minibatch step on the bf16 tcgen05 path, for WIDE nets (hidden widths multiples of 256; BASELINE.json
+ * configs[4]): forward with saved activations, dX and dW as tensor-core GEMMs (fp32 accumulate, psi kept in bf16),
+ * gradient in fp64, update / re-forward / accept-or-roll-back exactly as above on the fp64 master weights.
+ * Stated tolerance vs the fp64 rule: relative L2 error of each layer's dW <= 3e-2 (tests/test_tc_gpu.py). */
+CAB_API int cab_train_batch_bf16_host(cab_net *net, const int8_t *codes_host, const double *targets_host, long n_cases,
+                              double *lambda, double max_const, double rate, int *accepted, double *err, double *new_err);
+CAB_API int cab_train_batch_bf16_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases,
+                             double *lambda, double max_const, double rate, int *accepted, double *err, double *new_err,
+                             void *stream);
+/* forward + backward only: sum_b dW into cab_grad_buffer()[0..nw), then sum_b E, unused, count */
+CAB_API int cab_grad_bf16_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases, void *stream);
 /* Optimizer::dropout ("weak dilution", network.cpp:281-292): each weight w.p. rate -> U(-1,1), Philox(seed, offset). */
 CAB_API int cab_dropout(cab_net *net, double rate, uint64_t seed, uint64_t offset, long *hits);
 

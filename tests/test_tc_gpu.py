@@ -68,3 +68,60 @@ def test_wide_net_is_refused_by_the_fp64_stream_kernel(cab, golden):
     with pytest.raises(cab.CabError) as e:
         net.predict_batch(golden["syn_codes"][:8])
     assert e.value.code == cab.CAB_EINVAL and "bf16" in str(e.value)
+
+
+# ---- bf16 tcgen05 training step (forward with saved activations, dX / dW GEMMs) vs the fp64 rule ---------------------
+# Stated tolerance: per layer, ||dW_bf16 - dW_fp64||_2 <= 3e-2 * ||dW_fp64||_2 (bf16 activations and psi, fp32
+# accumulation over the batch, fp64 update on the master weights); E within 2e-2 relative.
+DW_RTOL = 3e-2
+
+
+def _layer_slices(dims):
+    off = 0
+    for k, n in zip(dims[:-1], dims[1:]):
+        yield slice(off, off + k * n)
+        off += k * n
+
+
+@pytest.mark.parametrize("dims,n", [([64, 256, 256, 1], 300), ([64, 512, 256, 1], 1000), ([64, 256, 512, 256, 1], 64),
+                                    ([64, 2048, 2048, 2048, 2048, 1], 96)])
+def test_bf16_train_step_vs_fp64_oracle(cab, port, golden, dims, n):
+    w = scaled_weights(dims, sum(dims) + 1)
+    codes = np.ascontiguousarray(np.tile(golden["syn_codes"], (2, 1))[:n])
+    rng = np.random.default_rng(n)
+    targets = np.clip(rng.normal(0.0, 1.5, n), -3.9, 3.9)
+    lam = 2e-3
+    onet = port.net_from_weights(dims, w)
+    o_acc, o_lam, o_e0, o_e1 = onet.train_batch(codes, targets, lam)
+    net = cab.Network.from_weights(dims, w)
+    g_lam, g_acc, g_e0, g_e1 = cab.Optimizer.train_batch_bf16(net, codes, targets, lam)
+    assert abs(g_e0 - o_e0) <= 2e-2 * o_e0 and abs(g_e1 - o_e1) <= 2e-2 * o_e1
+    assert g_acc == bool(o_acc) and g_lam == o_lam
+    assert g_acc, "a small step must be accepted, otherwise there is no update to compare"
+    dw_g, dw_o = net.get_weights() - w, onet.get_weights() - w
+    for l, sl in enumerate(_layer_slices(dims)):
+        num, den = np.linalg.norm(dw_g[sl] - dw_o[sl]), np.linalg.norm(dw_o[sl])
+        assert den > 0 and num <= DW_RTOL * den, (l, num / den)
+
+
+def test_bf16_training_reduces_the_error_and_tracks_the_fp64_trainer(cab, golden):
+    dims = [64, 256, 256, 1]
+    w = scaled_weights(dims, 9)
+    codes = golden["syn_codes"][:2048]
+    teacher = cab.Network.from_weights(dims, scaled_weights(dims, 10))
+    targets = teacher.predict_batch(codes)
+    a, b = cab.Network.from_weights(dims, w), cab.Network.from_weights(dims, w)
+    lam_a = lam_b = 0.5
+    first = last_a = last_b = None
+    for _ in range(30):
+        lam_a, _, e0, e1a = cab.Optimizer.train_batch_bf16(a, codes, targets, lam_a)
+        lam_b, _, _, e1b = cab.Optimizer.train_batch(b, codes, targets, lam_b)
+        first = e0 if first is None else first
+        last_a, last_b = e1a, e1b
+    assert last_a < 0.7 * first and abs(last_a - last_b) < 0.15 * last_b
+
+
+def test_bf16_trainer_refuses_the_default_net(cab, golden):
+    net = cab.Network.from_weights([64, 144, 225, 100, 1], golden["latest_weights"])
+    with pytest.raises(cab.CabError):
+        cab.Optimizer.train_batch_bf16(net, golden["syn_codes"][:64], np.zeros(64), 2.0)
