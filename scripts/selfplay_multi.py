@@ -1,0 +1,42 @@
+"""BASELINE.json configs[2] on N GPUs: one self-play process per GPU (independent games, replicated weights, no
+collective), host threads split evenly. Aggregate = total work / slowest process time.
+
+    python scripts/selfplay_multi.py N_GPUS [games_per_gpu] [playouts] [moves] [in_flight] [network_priors]
+"""
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    games, playouts, moves, in_flight, priors = (int(sys.argv[i]) if len(sys.argv) > i else d
+                                                 for i, d in ((2, 512), (3, 800), (4, 2), (5, 1024), (6, 1)))
+    cab = importlib.import_module("chess-ai_b200")
+    latest = os.path.join(tempfile.mkdtemp(), "latest.txt")
+    cab.Network.from_weights([64, 144, 225, 100, 1], np.fromfile(os.path.join(ROOT, "tests", "golden", "latest_weights.f64"), dtype="<f8")).dump(latest)
+    threads = max(1, (os.cpu_count() or 16) // n)
+    exe = os.path.join(ROOT, "chess-ai_b200", "lib", "selfplay")
+    procs = [subprocess.Popen([exe, latest, str(games), str(playouts), str(moves), str(threads), str(in_flight), str(priors), str(d), str(1000 + d)],
+                              stdout=subprocess.PIPE) for d in range(n)]
+    outs = [json.loads(p.communicate()[0].decode().strip().splitlines()[-1]) for p in procs]
+    assert all(p.returncode == 0 for p in procs)
+    secs = max(o["seconds"] for o in outs)
+    tot = {k: sum(o[k] for o in outs) for k in ("playouts", "boards_evaluated", "moves_played", "flushes", "gpu_launches")}
+    print(json.dumps({"config": "configs[2]: MCTS self-play, one process per GPU, no collective", "n_gpus": n, "host_cpus": os.cpu_count(),
+                      "threads_per_gpu": threads, "games_per_gpu": games, "playouts_per_move": playouts, "moves_per_game": moves,
+                      "in_flight_per_thread": in_flight, "network_priors": priors, "seconds_slowest": secs,
+                      "playouts_per_s": round(tot["playouts"] / secs, 1), "positions_evaluated_per_s": round(tot["boards_evaluated"] / secs, 1),
+                      "avg_boards_per_flush": round(tot["boards_evaluated"] / max(1, tot["flushes"]), 1), "per_gpu_boards_per_s": [round(o["boards_per_s"], 1) for o in outs]}))
+
+
+if __name__ == "__main__":
+    main()
