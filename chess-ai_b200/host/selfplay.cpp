@@ -47,6 +47,8 @@ struct Node {
   uint16_t n_children = 0;
   int8_t color = 1;
   bool expanded = false;
+  int8_t state = 0;                // 0 = not examined, 1 = the side to move has a legal move, 2 = game over here
+  int8_t result = 0;               // winner when state == 2 (0 = draw)
   Move move{0, 0, 0};
   double value() const { const int n = visits - vloss; return n > 0 ? value_sum / n : 0.0; }
 };
@@ -85,15 +87,36 @@ struct Worker {
   std::mt19937_64 rng;
   Stats st;
 
-  double puct(const Node &parent, const Node &child) const {
-    double base = std::log((parent.visits + 19652.0 + 1.0) / 19652.0) + 1.25;
-    base *= std::sqrt((double) parent.visits) / (child.visits + 1);
-    return base * child.prior + child.value();
+  // tree.cpp:276-283; the parent-only factor is hoisted out of the loop over children
+  static double puct_parent(const Node &parent) {
+    return (std::log((parent.visits + 19652.0 + 1.0) / 19652.0) + 1.25) * std::sqrt((double) parent.visits);
+  }
+  static double puct(double parent_factor, const Node &child) {
+    return parent_factor / (child.visits + 1) * child.prior + child.value();
   }
 
-  void request_expansion(Playout &p) {
+  // Game::tryMove without the mate / stalemate scan (game.cpp:847-871): that scan is a full move generation, which
+  // the node below repeats anyway when it is expanded; its outcome is cached in Node::state instead.
+  static void play_lazy(Position &p, Move mv) {
+    const bool capture = apply_move(p.sq, mv);
+    p.side = (int8_t) -p.side;
+    p.no_capture = capture ? 0 : p.no_capture + 1;
+    if (p.no_capture >= 50) { p.over = 1; p.result = 0; }
+  }
+  static void mark_over(Position &pos, Node &n) {     // Game::updateGameState (game.cpp:872-890) for "no legal move"
+    const int ks = king_square(pos.sq, pos.side);
+    const bool safe = ks < 0 || !attacked(pos.sq, ks >> 3, ks & 7, pos.side);
+    n.state = 2;
+    n.result = safe ? 0 : (int8_t) -pos.side;
+    pos.over = 1;
+    pos.result = n.result;
+  }
+
+  // false: the side to move has no legal move (nothing queued)
+  bool request_expansion(Playout &p) {
     Move mv[kMaxMoves];
     const int n = generate_moves(p.pos, p.pos.side, mv, /*queen_only=*/true);   // std::map<Move> keeps one promotion (Q8)
+    if (n == 0) return false;
     static thread_local int8_t buf[(kMaxMoves + 1) * 64];
     std::memcpy(buf, p.pos.sq, 64);
     int n_boards = 1;
@@ -113,6 +136,7 @@ struct Worker {
     p.n_pending = n;
     if (cab_leafq_push(q, buf, n_boards, &p.slot) != CAB_OK) { std::fprintf(stderr, "%s\n", cab_last_error()); std::exit(1); }
     ++st.expansions;
+    return true;
   }
 
   void finish_expansion(Playout &p, const double *res) {
@@ -156,22 +180,34 @@ struct Worker {
     while (p.depth < kSearchDepth) {
       if (p.pos.over) break;
       Node &n = g.arena[p.node];
+      if (n.state == 2) { p.pos.over = 1; p.pos.result = n.result; break; }
       if (!n.expanded) {
-        request_expansion(p);
+        if (!request_expansion(p)) { mark_over(p.pos, n); break; }
+        n.state = 1;
         for (int i = 0; i < p.path_len; ++i) { g.arena[p.path[i]].visits += 1; g.arena[p.path[i]].vloss += 1; }
         return false;
       }
       int best = -1;
       double max_score = -1.0;
+      const double pf = puct_parent(n);
       for (int i = 0; i < n.n_children; ++i) {
-        const double s = puct(n, g.arena[n.first_child + i]);
+        const double s = puct(pf, g.arena[n.first_child + i]);
         if (s > max_score) { max_score = s; best = n.first_child + i; }
       }
       if (best < 0) break;
-      play(p.pos, g.arena[best].move);
+      play_lazy(p.pos, g.arena[best].move);
       p.node = best;
       p.path[p.path_len++] = best;
       ++p.depth;
+    }
+    if (!p.pos.over) {                         // depth limit reached: the leaf-value rule needs to know whether the game ended
+      Node &n = g.arena[p.node];
+      if (n.state == 2) { p.pos.over = 1; p.pos.result = n.result; }
+      else if (n.state == 0) {
+        Move tmp[kMaxMoves];
+        if (generate_moves(p.pos, p.pos.side, tmp, true) == 0) mark_over(p.pos, n);
+        else n.state = 1;
+      }
     }
     const double cc = p.pos.side;
     double value;
@@ -249,8 +285,9 @@ struct Worker {
           const Node &root = g.arena[0];
           int best = -1;
           double max_score = -1.0;
+          const double pf = puct_parent(root);
           for (int i = 0; i < root.n_children; ++i) {
-            const double s = puct(root, g.arena[root.first_child + i]);
+            const double s = puct(pf, g.arena[root.first_child + i]);
             if (s > max_score) { max_score = s; best = root.first_child + i; }
           }
           if (best >= 0) play(g.pos, g.arena[best].move);
