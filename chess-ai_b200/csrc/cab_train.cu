@@ -119,26 +119,67 @@ static int ensure_host_staging(cab_net *net, long n) {
 }
 
 // grad tasks (layer x tile blocks), built once per net and cached on the device
-struct GradPlan { GradTask *d_tasks = nullptr; int n_tasks = 0; };
+struct GradPlan {
+  GradTask *d_tasks = nullptr;
+  int n_tasks = 0;
+  std::vector<GradTask> tasks;
+  GradItem *d_items = nullptr;   // work items for `items_n` boards (rebuilt when the batch size changes)
+  int n_items = 0;
+  long items_n = -1;
+};
 static std::mutex g_plan_mu;
 static std::vector<std::pair<cab_net *, GradPlan>> g_grad_plans;
 
-static int get_grad_plan(cab_net *net, GradPlan *out) {
+// Splits n boards (rounded up to 4) of every task into warp-sized items of about equal DMMA work: a task's number of
+// slices is proportional to its tile count. Board ranges start on stage boundaries (multiples of kGradStageBoards).
+static int build_grad_items(cab_net *net, GradPlan &gp, long n) {
+  if (gp.items_n == n) return CAB_OK;
+  const long n4 = (n + 3) / 4 * 4;
+  double wsum = 0.0;
+  // cost model of a block per board: its DMMAs, but never less than the copy-latency floor of a thin block
+  auto cost = [](const GradTask &t) { return std::max(t.nkt * t.nnt + 2.0, 10.0); };
+  for (auto &t : gp.tasks) wsum += cost(t);
+  const double target_items = (double) net->sm_count * kGradWarps * 4;
+  std::vector<GradItem> items;
+  for (int ti = 0; ti < gp.n_tasks; ++ti) {
+    const GradTask &t = gp.tasks[ti];
+    long slices = std::max<long>(1, std::lround(target_items * cost(t) / wsum));
+    long per = std::max<long>(64, (n4 + slices - 1) / slices);
+    per = (per + kGradStageBoards - 1) / kGradStageBoards * kGradStageBoards;
+    for (long b = 0; b < n4; b += per) items.push_back(GradItem{ti, (int) b, (int) std::min(b + per, n4), 0});
+  }
+  cudaFree(gp.d_items);
+  gp.d_items = nullptr;
+  CAB_CUDA(cudaMalloc(&gp.d_items, items.size() * sizeof(GradItem)));
+  CAB_CUDA(cudaMemcpy(gp.d_items, items.data(), items.size() * sizeof(GradItem), cudaMemcpyHostToDevice));
+  gp.n_items = (int) items.size();
+  gp.items_n = n;
+  return CAB_OK;
+}
+
+static int get_grad_plan(cab_net *net, long n, GradPlan *out) {
   std::lock_guard<std::mutex> lk(g_plan_mu);
   for (auto &p : g_grad_plans)
-    if (p.first == net) { *out = p.second; return CAB_OK; }
+    if (p.first == net) {
+      int rc = build_grad_items(net, p.second, n);
+      *out = p.second;
+      return rc;
+    }
   std::vector<GradTask> tasks;
   const int L = (int) net->dims.size();
   for (int l = 0; l + 1 < L; ++l) {
     const int K = net->dims[l], N = net->dims[l + 1];
     const int kt = (K + 7) / 8, nt = (N + 7) / 8;
-    for (int k0 = 0; k0 < kt; k0 += kGK)
-      for (int n0 = 0; n0 < nt; n0 += kGN) {
+    // even split of the tile grid into blocks of at most kGK x kGN tiles (18 -> 4,4,4,3,3 rather than 4,4,4,4,2)
+    const int gk = (kt + kGK - 1) / kGK, gn = (nt + kGN - 1) / kGN;
+    for (int bk = 0; bk < gk; ++bk)
+      for (int bn = 0; bn < gn; ++bn) {
+        const int k0 = kt * bk / gk, k1 = kt * (bk + 1) / gk, n0 = nt * bn / gn, n1 = nt * (bn + 1) / gn;
         GradTask t{};
         t.a_unit = net->act_unit_off[l] + k0;
         t.p_unit = net->act_unit_off[l + 1] + n0;
-        t.nkt = std::min(kGK, kt - k0);
-        t.nnt = std::min(kGN, nt - n0);
+        t.nkt = k1 - k0;
+        t.nnt = n1 - n0;
         t.k0 = k0 * 8; t.n0 = n0 * 8;
         t.K = K; t.N = N;
         t.w_off = net->woff[l];
@@ -149,9 +190,11 @@ static int get_grad_plan(cab_net *net, GradPlan *out) {
   gp.n_tasks = (int) tasks.size();
   CAB_CUDA(cudaMalloc(&gp.d_tasks, tasks.size() * sizeof(GradTask)));
   CAB_CUDA(cudaMemcpy(gp.d_tasks, tasks.data(), tasks.size() * sizeof(GradTask), cudaMemcpyHostToDevice));
+  gp.tasks = tasks;
+  int rc = build_grad_items(net, gp, n);
   g_grad_plans.push_back({net, gp});
   *out = gp;
-  return CAB_OK;
+  return rc;
 }
 
 void drop_grad_plan(cab_net *net) {
@@ -159,6 +202,7 @@ void drop_grad_plan(cab_net *net) {
   for (size_t i = 0; i < g_grad_plans.size(); ++i)
     if (g_grad_plans[i].first == net) {
       cudaFree(g_grad_plans[i].second.d_tasks);
+      cudaFree(g_grad_plans[i].second.d_items);
       g_grad_plans.erase(g_grad_plans.begin() + i);
       return;
     }
@@ -197,24 +241,31 @@ static int launch_backward(cab_net *net, const double *d_targets, long b0, long 
 
 static int launch_grad(cab_net *net, long n, cudaStream_t stream) {
   GradPlan gp;
-  int rc = get_grad_plan(net, &gp);
+  int rc = get_grad_plan(net, n, &gp);
   if (rc != CAB_OK) return rc;
   GradArgs a{};
   a.tasks = gp.d_tasks;
-  a.n_tasks = gp.n_tasks;
-  a.n_boards_pad4 = (n + 3) / 4 * 4;
-  // enough (task, slice) warps to cover the chip a few times, slices of >= 64 boards
-  long slices = std::max<long>(1, (long) net->sm_count * 16 / std::max(1, gp.n_tasks));
-  long slice_boards = std::max<long>(64, (a.n_boards_pad4 + slices - 1) / slices);
-  slice_boards = (slice_boards + 3) / 4 * 4;
-  a.n_slices = (int) ((a.n_boards_pad4 + slice_boards - 1) / slice_boards);
-  a.slice_boards = slice_boards;
+  a.items = gp.d_items;
+  a.n_items = gp.n_items;
+  static const int env_warps = getenv("CAB_GRAD_WARPS") ? atoi(getenv("CAB_GRAD_WARPS")) : kGradWarps;
+  static const int env_stages = getenv("CAB_GRAD_STAGES") ? atoi(getenv("CAB_GRAD_STAGES")) : kGradStages;
+  a.n_warps = std::max(1, std::min(env_warps, kGradWarps));
+  a.n_stages = std::max(2, env_stages);
+  const size_t smem = (size_t) a.n_warps * a.n_stages * kGradStageBytes + (size_t) a.n_warps * 8 * sizeof(uint64_t);
+  if (smem > 227 * 1024) { set_error("grad kernel geometry needs %zu bytes of shared memory", smem); return CAB_EINVAL; }
   a.acts = net->d_acts;
   a.psis = net->d_psis;
   a.save_stride = net->train_cap * 8;
   a.grad = net->d_grad;
-  const long warps = (long) a.n_tasks * a.n_slices;
-  grad_kernel<<<(int) ((warps + 3) / 4), 128, 0, stream>>>(a);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CAB_CUDA(cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  a.next_item = reinterpret_cast<int *>(net->d_scalars + 16);
+  CAB_CUDA(cudaMemsetAsync(a.next_item, 0, sizeof(int), stream));
+  const int grid = std::min((a.n_items + a.n_warps - 1) / a.n_warps, net->sm_count);
+  grad_kernel<<<grid, a.n_warps * 32, smem, stream>>>(a);
   net->launches++;
   CAB_CUDA(cudaGetLastError());
   return CAB_OK;

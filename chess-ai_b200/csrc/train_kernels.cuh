@@ -291,11 +291,20 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
 
 // ---------------------------------------------------------------------------------------------------------------
 // minibatch: weight gradient  G_l[k][n] += sum_b a_l[b][k] * psi_{l+1}[b][n]
-// One warp owns a block of up to kGK x kGN 8x8 tiles of one layer and a slice of the boards; per step of 4 boards it
-// loads kGK A fragments + kGN B fragments (256 contiguous bytes each: the unit layout is [unit][board][8]) and
-// issues kGK*kGN DMMAs (M = k features, N = n features, K = boards).
+// One warp owns a block of up to kGK x kGN 8x8 tiles of one layer and a slice of the boards (an "item"); per step of
+// 4 boards it needs kGK A fragments + kGN B fragments (256 contiguous bytes each: the unit layout is
+// [unit][board][8]) and issues kGK*kGN DMMAs (M = k features, N = n features, K = boards).
+// The fragments reach the warp through its PRIVATE shared-memory ring: kGradStages stages of kGradStageBoards boards,
+// each filled by one 1-D TMA bulk copy per unit (1 KB) completing on the stage's mbarrier. With plain global loads
+// the kernel sat on long_scoreboard (ncu: 5.0 of 8.4 stalled warps per issue, DMMA pipe 52 % active on 8 warps/SM).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kGK = 4, kGN = 8;
+constexpr int kGradWarps = 8;               // per CTA (default; GradArgs::n_warps), one CTA per SM
+constexpr int kGradStageBoards = 16;        // 4 DMMA steps
+constexpr int kGradStages = 2;              // default; GradArgs::n_stages
+constexpr int kGradUnitBytes = kGradStageBoards * 64;                       // one unit of one stage
+constexpr int kGradStageBytes = (kGK + kGN) * kGradUnitBytes;               // 12 KB
+constexpr size_t kGradSmem = (size_t) kGradWarps * kGradStages * kGradStageBytes + kGradWarps * kGradStages * sizeof(uint64_t);
 struct GradTask {
   uint32_t a_unit, p_unit;   // first unit of the k-tiles inside acts, of the n-tiles inside psis
   int nkt, nnt;              // tiles in this block (<= kGK, <= kGN)
@@ -303,71 +312,125 @@ struct GradTask {
   int K, N;                  // layer shape
   long w_off;
 };
+struct GradItem {            // one warp's work: a task and a board range (multiple of 4 boards)
+  int task;
+  int b_lo, b_hi;
+  int pad;
+};
 struct GradArgs {
   const GradTask *tasks;
-  int n_tasks;
-  int n_slices;
-  long slice_boards;         // multiple of 4
-  long n_boards_pad4;        // boards rounded up to 4
+  const GradItem *items;
+  int n_items;
+  int n_warps, n_stages;
+  int *next_item;            // global work counter, zeroed before the launch
   const double *acts, *psis;
   long save_stride;
   double *grad;
 };
 
-__global__ void __launch_bounds__(128) grad_kernel(const GradArgs args) {
-  const int warp_global = (int) ((blockIdx.x * (long) blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (warp_global >= args.n_tasks * args.n_slices) return;
-  const GradTask t = args.tasks[warp_global / args.n_slices];
-  const int slice = warp_global % args.n_slices;
-  const long b_lo = slice * args.slice_boards, b_hi = min(b_lo + args.slice_boards, args.n_boards_pad4);
-  double acc[kGK][kGN][2];
+// One item with a compile-time block shape: no predicates around the DMMAs (the runtime-shaped loop spent 4-5
+// instructions per DMMA on predicate logic and issued at 22 cycles per DMMA instead of 16).
+template <int NKT, int NNT>
+__device__ __forceinline__ void grad_item(const GradArgs &args, const GradItem &it, const GradTask &t, uint8_t *ring, uint64_t *full,
+                                          uint32_t &parity_bits, int ring_units, int lane) {
+  constexpr int n_units = NKT + NNT;
+  constexpr uint32_t stage_bytes = (uint32_t) n_units * kGradUnitBytes;   // stages packed tightly: thin blocks get a deeper ring
+  const int item_stages = min(ring_units / n_units, 8);
+  // lane u < n_units copies unit u of a stage (A units first, then B units), 1 KB each
+  const double *my_src = nullptr;
+  if (lane < n_units)
+    my_src = lane < NKT ? args.acts + (size_t) (t.a_unit + lane) * args.save_stride
+                        : args.psis + (size_t) (t.p_unit + (lane - NKT)) * args.save_stride;
+  auto fill = [&](int stage, long board0) {
+    if (lane == 0) mbar_arrive_expect_tx(&full[stage], stage_bytes);
+    __syncwarp();
+    if (lane < n_units)
+      bulk_g2s(ring + (size_t) stage * stage_bytes + (size_t) lane * kGradUnitBytes, my_src + (size_t) board0 * 8, kGradUnitBytes, &full[stage]);
+  };
+  const int n_stage_iters = (it.b_hi - it.b_lo + kGradStageBoards - 1) / kGradStageBoards;
+  for (int s = 0; s < item_stages && s < n_stage_iters; ++s) fill(s, it.b_lo + (long) s * kGradStageBoards);
+
+  double acc[NKT][NNT][2];
 #pragma unroll
-  for (int i = 0; i < kGK; ++i)
+  for (int i = 0; i < NKT; ++i)
 #pragma unroll
-    for (int j = 0; j < kGN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NNT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   // lane (r = lane>>2, c = lane&3): A[k = 8kt + r][board b + c], B[board b + c][n = 8nt + r]
-  const size_t lane_off = (size_t) (lane & 3) * 8 + (lane >> 2);
-  // fragment pointers of this lane (unused tile slots point at slot 0 and are multiplied into nothing)
-  const double *ap[kGK], *bp[kGN];
+  const uint32_t lane_off = (uint32_t) ((lane & 3) * 64 + (lane >> 2) * 8);
+  int stage = 0;
+  for (int si = 0; si < n_stage_iters; ++si) {
+    const uint8_t *base = ring + (size_t) stage * stage_bytes + lane_off;
+    mbar_wait(&full[stage], (parity_bits >> stage) & 1u);
+    parity_bits ^= 1u << stage;
+    const int steps = min(kGradStageBoards / 4, (it.b_hi - (it.b_lo + si * kGradStageBoards)) / 4);
+    double af[NKT], bf[NNT], an[NKT], bn[NNT];
 #pragma unroll
-  for (int i = 0; i < kGK; ++i) ap[i] = args.acts + (size_t) (t.a_unit + (i < t.nkt ? i : 0)) * args.save_stride + lane_off;
+    for (int i = 0; i < NKT; ++i) af[i] = *reinterpret_cast<const double *>(base + i * kGradUnitBytes);
 #pragma unroll
-  for (int j = 0; j < kGN; ++j) bp[j] = args.psis + (size_t) (t.p_unit + (j < t.nnt ? j : 0)) * args.save_stride + lane_off;
-  // software pipeline: the 12 fragment loads of step b+4 are in flight while the 32 DMMAs of step b issue
-  double af[kGK], bf[kGN], an[kGK], bn[kGN];
+    for (int j = 0; j < NNT; ++j) bf[j] = *reinterpret_cast<const double *>(base + (NKT + j) * kGradUnitBytes);
+    for (int st = 0; st < steps; ++st) {
+      const int nx = st + 1 < steps ? st + 1 : st;
 #pragma unroll
-  for (int i = 0; i < kGK; ++i) af[i] = __ldg(ap[i] + (size_t) b_lo * 8);
+      for (int i = 0; i < NKT; ++i) an[i] = *reinterpret_cast<const double *>(base + i * kGradUnitBytes + nx * 256);
 #pragma unroll
-  for (int j = 0; j < kGN; ++j) bf[j] = __ldg(bp[j] + (size_t) b_lo * 8);
-  for (long b = b_lo; b < b_hi; b += 4) {
-    const long nb = b + 4 < b_hi ? b + 4 : b;
+      for (int j = 0; j < NNT; ++j) bn[j] = *reinterpret_cast<const double *>(base + (NKT + j) * kGradUnitBytes + nx * 256);
 #pragma unroll
-    for (int i = 0; i < kGK; ++i) an[i] = __ldg(ap[i] + (size_t) nb * 8);
+      for (int i = 0; i < NKT; ++i)
 #pragma unroll
-    for (int j = 0; j < kGN; ++j) bn[j] = __ldg(bp[j] + (size_t) nb * 8);
+        for (int j = 0; j < NNT; ++j) dmma884(acc[i][j], af[i], bf[j]);
 #pragma unroll
-    for (int i = 0; i < kGK; ++i)
+      for (int i = 0; i < NKT; ++i) af[i] = an[i];
 #pragma unroll
-      for (int j = 0; j < kGN; ++j)
-        if (i < t.nkt && j < t.nnt) dmma884(acc[i][j], af[i], bf[j]);
-#pragma unroll
-    for (int i = 0; i < kGK; ++i) af[i] = an[i];
-#pragma unroll
-    for (int j = 0; j < kGN; ++j) bf[j] = bn[j];
+      for (int j = 0; j < NNT; ++j) bf[j] = bn[j];
+    }
+    __syncwarp();                               // every lane has its fragments in registers: the stage may be refilled
+    if (si + item_stages < n_stage_iters) fill(stage, it.b_lo + (long) (si + item_stages) * kGradStageBoards);
+    if (++stage == item_stages) stage = 0;
   }
   // C[row = lane>>2][col = 2*(lane&3) + {0,1}] -> G[k][n]
 #pragma unroll
-  for (int i = 0; i < kGK; ++i)
+  for (int i = 0; i < NKT; ++i)
 #pragma unroll
-    for (int j = 0; j < kGN; ++j) {
-      if (i >= t.nkt || j >= t.nnt) continue;
+    for (int j = 0; j < NNT; ++j) {
       const int k = t.k0 + 8 * i + (lane >> 2), nn = t.n0 + 8 * j + 2 * (lane & 3);
       if (k < t.K) {
         if (nn < t.N) atomicAdd(args.grad + t.w_off + (long) k * t.N + nn, acc[i][j][0]);
         if (nn + 1 < t.N) atomicAdd(args.grad + t.w_off + (long) k * t.N + nn + 1, acc[i][j][1]);
       }
     }
+}
+
+__global__ void __launch_bounds__(kGradWarps * 32, 1) grad_kernel(const GradArgs args) {
+  extern __shared__ __align__(128) uint8_t grad_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_warps = args.n_warps, n_stages = args.n_stages;
+  uint8_t *ring = grad_smem + (size_t) warp * n_stages * kGradStageBytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(grad_smem + (size_t) n_warps * n_stages * kGradStageBytes) + warp * 8;
+  if (lane == 0) {
+    for (int s = 0; s < 8; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const int ring_units = n_stages * (kGK + kGN);   // ring capacity in 1 KB unit slots
+  uint32_t parity_bits = 0;                        // per-stage phase parity of this warp's mbarriers
+  // persistent warps: each one draws items from a global counter until none are left (no CTA-wide barrier anywhere)
+  for (;;) {
+    int item_idx = 0;
+    if (lane == 0) item_idx = atomicAdd(args.next_item, 1);
+    item_idx = __shfl_sync(0xffffffffu, item_idx, 0);
+    if (item_idx >= args.n_items) break;
+    const GradItem it = args.items[item_idx];
+    const GradTask t = args.tasks[it.task];
+#define CAB_GRAD_CASE(A, B) case (A) * 16 + (B): grad_item<A, B>(args, it, t, ring, full, parity_bits, ring_units, lane); break;
+#define CAB_GRAD_ROW(A) CAB_GRAD_CASE(A, 1) CAB_GRAD_CASE(A, 2) CAB_GRAD_CASE(A, 3) CAB_GRAD_CASE(A, 4) \
+                        CAB_GRAD_CASE(A, 5) CAB_GRAD_CASE(A, 6) CAB_GRAD_CASE(A, 7) CAB_GRAD_CASE(A, 8)
+    switch (t.nkt * 16 + t.nnt) {
+      CAB_GRAD_ROW(1) CAB_GRAD_ROW(2) CAB_GRAD_ROW(3) CAB_GRAD_ROW(4)
+      default: break;
+    }
+#undef CAB_GRAD_ROW
+#undef CAB_GRAD_CASE
+  }
 }
 
 // dW = (lambda / count) * G ; W += dW     (batch mean of network.cpp:258-259). count = grad[n + 2].
