@@ -25,7 +25,7 @@ constexpr int kConsumerWarps = 16;                      // max warps per CTA; a 
 constexpr int kMaxThreads = kConsumerWarps * 32;        // no producer warp: the last warp off a ring slot re-arms it
 constexpr int kBoardsPerWarp = 8;                       // boards per warp pair (one DMMA M tile)
 constexpr int kMaxStages = 8;                           // weight ring depth upper bound
-constexpr int kStageBytes = 49152;                      // default ring slot (measured best: 2 x 48 KB with 8 pairs)
+constexpr int kStageBytes = 53248;                      // default ring slot (measured best: 2 x 52 KB with 8 pairs)
 constexpr int kMaxNB = 32;                              // output tiles of one n-block (split over the pair)
 constexpr int kMaxNBH = 16;                             // output tiles one warp accumulates in registers
 constexpr int kUnitBytes = 512;                         // 32 lanes x double2

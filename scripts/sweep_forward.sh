@@ -1,8 +1,8 @@
-python -m pytest tests/test_forward_gpu.py -m gpu -x -q 2>&1 | tail -3
-for cfg in "8 6 4" "8 6 8" "8 6 2" "4 3 4" "4 3 8" "4 8 4" "8 4 4"; do
+# forward-kernel geometry sweep: ring slot size (KB) x ring depth x host streams, through bench.py
+for cfg in "48 2 4" "32 3 4" "34 3 4" "52 2 4" "40 2 4" "24 4 4" "48 2 6" "48 2 3" "48 2 8"; do
   set -- $cfg
-  echo "== warps=$1 stages=$2 streams=$3"
-  CAB_FWD_WARPS=$1 CAB_FWD_STAGES=$2 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --streams $3 2>&1 | python -c "
+  echo "== slot_kb=$1 stages=$2 streams=$3"
+  CAB_STAGE_KB=$1 CAB_FWD_STAGES=$2 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-train --streams $3 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: j=json.loads(l)
