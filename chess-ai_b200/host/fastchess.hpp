@@ -129,6 +129,22 @@ inline bool leaves_king_safe(const Position &p, int from, int to) {
   return !attacked(tmp, ks >> 3, ks & 7, color);
 }
 
+// The same predicate for a NON-king piece when the king (on ks, not in check now) is known: moving a piece can only
+// uncover a sliding attack, and only through the square it leaves; landing on a square or capturing can block or
+// remove attackers but never add one. So a piece that does not share a rank, file or diagonal with the king passes
+// without the simulation; everything else (aligned pieces, any move while in check, king moves) is simulated.
+inline bool leaves_king_safe_known_king(const Position &p, int from, int to, int ks, int color) {   // non-king piece
+  int8_t tmp[64];
+  std::memcpy(tmp, p.sq, 64);
+  tmp[to] = tmp[from];
+  tmp[from] = 0;
+  return !attacked(tmp, ks >> 3, ks & 7, color);
+}
+inline bool aligned(int a, int b) {
+  const int dr = (a >> 3) - (b >> 3), dc = (a & 7) - (b & 7);
+  return dr == 0 || dc == 0 || dr == dc || dr == -dc;
+}
+
 // pseudo-legal targets of the piece on `from` as a 64-bit mask (the piece's verifyMove + "not onto an own piece")
 inline uint64_t targets(const Position &p, int from) {
   const int8_t *sq = p.sq;
@@ -197,15 +213,20 @@ inline uint64_t targets(const Position &p, int from) {
 // legal moves of `color` in the reference's generation order; all four promotions unless queen_only
 inline int generate_moves(const Position &p, int color, Move *out, bool queen_only = false) {
   int n = 0;
+  const int ks = king_square(p.sq, color);
+  const bool calm = ks >= 0 && !attacked(p.sq, ks >> 3, ks & 7, color);   // own king present and not in check
   for (int from = 0; from < 64; ++from) {
     const int k = p.sq[from];
     if (k == 0 || color_of(k) != color) continue;
     uint64_t m = targets(p, from);
     const bool pawn = kind_of(k) == 6;
+    const bool king = kind_of(k) == 1;
+    const bool needs_simulation = !(calm && !king && !aligned(from, ks));
     while (m) {
       const int to = __builtin_ctzll(m);
       m &= m - 1;
-      if (!leaves_king_safe(p, from, to)) continue;
+      // a non-king move never moves or captures an own king, so the scan inside leaves_king_safe would find ks again
+      if (needs_simulation && !(king || ks < 0 ? leaves_king_safe(p, from, to) : leaves_king_safe_known_king(p, from, to, ks, color))) continue;
       if (pawn && ((to >> 3) == 0 || (to >> 3) == 7)) {
         out[n++] = Move{(uint8_t) from, (uint8_t) to, 3};
         if (!queen_only) {
@@ -220,9 +241,23 @@ inline int generate_moves(const Position &p, int color, Move *out, bool queen_on
 }
 
 // Move::doMove (game.cpp:499-623) on the codes; returns true when a piece was captured
+// every moved2x flag falls (game.cpp:505-513): codes 9 -> 8 and -9 -> -8 on all 64 squares, eight squares per word.
+// z has 0x80 in every byte of v that equals the pattern byte (exact zero-byte test, no cross-byte carries).
+inline void clear_moved2x(int8_t *sq) {
+  constexpr uint64_t k7f = 0x7f7f7f7f7f7f7f7full, k01 = 0x0101010101010101ull;
+  for (int i = 0; i < 8; ++i) {
+    uint64_t v;
+    std::memcpy(&v, sq + 8 * i, 8);
+    const uint64_t a = v ^ (k01 * 0x09), b = v ^ (k01 * 0xf7);
+    const uint64_t za = ~(((a & k7f) + k7f) | a | k7f), zb = ~(((b & k7f) + k7f) | b | k7f);
+    if ((za | zb) == 0) continue;
+    v = v - (za >> 7) + (zb >> 7);     // 0x09 -> 0x08, 0xf7 -> 0xf8: no borrow or carry leaves the byte
+    std::memcpy(sq + 8 * i, &v, 8);
+  }
+}
+
 inline bool apply_move(int8_t *sq, Move mv) {
-  for (int i = 0; i < 64; ++i)
-    if (sq[i] == 9) sq[i] = 8; else if (sq[i] == -9) sq[i] = -8;      // every moved2x flag falls (:505-513)
+  clear_moved2x(sq);
   const int from = mv.from, to = mv.to, r1 = from >> 3, c1 = from & 7, r2 = to >> 3, c2 = to & 7;
   int k = sq[from];
   const int color = color_of(k);

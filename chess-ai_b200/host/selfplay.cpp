@@ -47,10 +47,18 @@ struct Node {
   uint16_t n_children = 0;
   int8_t color = 1;
   bool expanded = false;
+  bool pending = false;            // children allocated, their evaluations are in the queue
+  bool eval = false;               // (as a child) its board was sent to the network for the prior logit
   int8_t state = 0;                // 0 = not examined, 1 = the side to move has a legal move, 2 = game over here
   int8_t result = 0;               // winner when state == 2 (0 = draw)
   Move move{0, 0, 0};
   double value() const { const int n = visits - vloss; return n > 0 ? value_sum / n : 0.0; }
+};
+// The per-child part of the PUCT score, kept apart from the nodes and contiguous per sibling group: the selection loop
+// (the hottest loop on the host, ~30 children x 8 levels per playout over trees far larger than the caches) then
+// streams 16 bytes per child instead of a whole node.
+struct ChildStat {
+  double q = 0.0, u = 0.0;         // value() and prior / (visits + 1)
 };
 
 struct Playout {
@@ -58,15 +66,15 @@ struct Playout {
   int game = 0, node = 0, depth = 0;
   int path[kSearchDepth + 2];
   int path_len = 0;
-  long slot = -1;     // first queue slot of the pending expansion (parent board, then the children)
-  int n_pending = 0;  // children of the pending expansion
-  Move pending_moves[kMaxMoves];
-  bool child_eval[kMaxMoves];
+  long slot = -1;     // first queue slot of the expansion this playout requested (parent board, then the evaluated
+                      // children); -1 when it only waits for an expansion another playout requested
 };
 
 struct GameState {
   Position pos;
   std::vector<Node> arena;
+  std::vector<ChildStat> stat;     // parallel to arena
+  void refresh(int i) { const Node &n = arena[i]; stat[i].q = n.value(); stat[i].u = n.prior / (n.visits + 1); }
   int launched = 0, done = 0, moves_played = 0;
   bool finished = false;
   std::vector<cases::Case> kept;   // boards of this game awaiting the game result
@@ -74,6 +82,7 @@ struct GameState {
 
 struct Stats {
   long playouts = 0, boards = 0, flushes = 0, expansions = 0, moves = 0, max_flush = 0;
+  double flush_seconds = 0.0;    // time this thread spent inside cab_leafq_flush (waiting for the GPU)
 };
 
 struct Worker {
@@ -91,9 +100,7 @@ struct Worker {
   static double puct_parent(const Node &parent) {
     return (std::log((parent.visits + 19652.0 + 1.0) / 19652.0) + 1.25) * std::sqrt((double) parent.visits);
   }
-  static double puct(double parent_factor, const Node &child) {
-    return parent_factor / (child.visits + 1) * child.prior + child.value();
-  }
+  static double puct(double parent_factor, const ChildStat &child) { return parent_factor * child.u + child.q; }
 
   // Game::tryMove without the mate / stalemate scan (game.cpp:847-871): that scan is a full move generation, which
   // the node below repeats anyway when it is expanded; its outcome is cached in Node::state instead.
@@ -112,66 +119,70 @@ struct Worker {
     pos.result = n.result;
   }
 
-  // false: the side to move has no legal move (nothing queued)
+  // Allocates the node's children and queues their boards. false: the side to move has no legal move.
   bool request_expansion(Playout &p) {
     Move mv[kMaxMoves];
     const int n = generate_moves(p.pos, p.pos.side, mv, /*queen_only=*/true);   // std::map<Move> keeps one promotion (Q8)
     if (n == 0) return false;
+    GameState &g = games[p.game];
+    const int first = (int) g.arena.size();
+    g.arena.resize(g.arena.size() + n);
+    g.stat.resize(g.arena.size());
+    Node &parent = g.arena[p.node];
+    parent.first_child = first;
+    parent.n_children = (uint16_t) n;
+    parent.pending = true;
     static thread_local int8_t buf[(kMaxMoves + 1) * 64];
     std::memcpy(buf, p.pos.sq, 64);
     int n_boards = 1;
     for (int i = 0; i < n; ++i) {
-      Position c = p.pos;
-      apply_move(c.sq, mv[i]);
+      int8_t *dst = buf + n_boards * 64;
+      std::memcpy(dst, p.pos.sq, 64);
+      apply_move(dst, mv[i]);
       bool eval_child = network_priors;
       if (!eval_child) {                       // decider.cpp:52-57: the network is asked only when the opponent has no reply
-        Move tmp[kMaxMoves];
+        Position c;
+        std::memcpy(c.sq, dst, 64);
         c.side = (int8_t) -p.pos.side;
+        Move tmp[kMaxMoves];
         eval_child = generate_moves(c, c.side, tmp, true) == 0;
       }
-      p.pending_moves[i] = mv[i];
-      p.child_eval[i] = eval_child;
-      if (eval_child) { std::memcpy(buf + n_boards * 64, c.sq, 64); ++n_boards; }
+      Node &ch = g.arena[first + i];
+      ch.color = (int8_t) -parent.color;
+      ch.move = mv[i];
+      ch.eval = eval_child;
+      if (eval_child) ++n_boards;
     }
-    p.n_pending = n;
     if (cab_leafq_push(q, buf, n_boards, &p.slot) != CAB_OK) { std::fprintf(stderr, "%s\n", cab_last_error()); std::exit(1); }
     ++st.expansions;
     return true;
   }
 
   void finish_expansion(Playout &p, const double *res) {
+    if (p.slot < 0) return;                    // this playout only waited for somebody else's expansion
     GameState &g = games[p.game];
     Node &n = g.arena[p.node];
-    if (n.expanded) return;                    // a sibling playout parked on the same node got there first
     const double cm = n.color;
-    const int k = p.n_pending;
-    const int first = (int) g.arena.size();
-    g.arena.resize(g.arena.size() + k);
-    Node &nn = g.arena[p.node];                // the resize may have moved the arena
+    const int k = n.n_children, first = n.first_child;
     double sum = 0.0;
     long s = p.slot + 1;
     for (int i = 0; i < k; ++i) {
-      const double logit = p.child_eval[i] ? cm * res[s++] : cm * 20.0;
-      const double w = std::exp(cm * logit);   // tree.cpp:302
-      g.arena[first + i].prior = w;
-      sum += w;
-    }
-    for (int i = 0; i < k; ++i) {
       Node &c = g.arena[first + i];
-      c.prior /= sum;
-      c.color = (int8_t) -nn.color;
-      c.move = p.pending_moves[i];
+      const double logit = c.eval ? cm * res[s++] : cm * 20.0;
+      c.prior = std::exp(cm * logit);          // tree.cpp:302
+      sum += c.prior;
     }
-    nn.first_child = first;
-    nn.n_children = (uint16_t) k;
-    nn.expanded = true;
+    for (int i = 0; i < k; ++i) g.arena[first + i].prior /= sum;
     if (p.node == 0 && k > 0) {                // root: Dirichlet(0.2) noise, 25 % (tree.cpp:318-347)
       std::gamma_distribution<double> gamma(0.2, 1.0);
-      std::vector<double> th(k);
-      double tot = 0.0;
-      for (auto &t : th) { t = gamma(rng); tot += t; }
+      double th[kMaxMoves], tot = 0.0;
+      for (int i = 0; i < k; ++i) { th[i] = gamma(rng); tot += th[i]; }
       for (int i = 0; i < k; ++i) g.arena[first + i].prior = g.arena[first + i].prior * 0.75 + (th[i] / tot) * 0.25;
     }
+    for (int i = 0; i < k; ++i) g.refresh(first + i);
+    n.pending = false;
+    n.expanded = true;
+    p.slot = -1;
   }
 
   // advance until the playout parks (false) or completes (true)
@@ -182,16 +193,19 @@ struct Worker {
       Node &n = g.arena[p.node];
       if (n.state == 2) { p.pos.over = 1; p.pos.result = n.result; break; }
       if (!n.expanded) {
-        if (!request_expansion(p)) { mark_over(p.pos, n); break; }
-        n.state = 1;
-        for (int i = 0; i < p.path_len; ++i) { g.arena[p.path[i]].visits += 1; g.arena[p.path[i]].vloss += 1; }
+        p.slot = -1;
+        if (!n.pending) {                      // first playout to get here asks for the expansion, later ones just wait
+          if (!request_expansion(p)) { mark_over(p.pos, g.arena[p.node]); break; }
+          g.arena[p.node].state = 1;           // (the arena may have moved)
+        }
+        for (int i = 0; i < p.path_len; ++i) { Node &v = g.arena[p.path[i]]; v.visits += 1; v.vloss += 1; g.refresh(p.path[i]); }
         return false;
       }
       int best = -1;
       double max_score = -1.0;
       const double pf = puct_parent(n);
       for (int i = 0; i < n.n_children; ++i) {
-        const double s = puct(pf, g.arena[n.first_child + i]);
+        const double s = puct(pf, g.stat[n.first_child + i]);
         if (s > max_score) { max_score = s; best = n.first_child + i; }
       }
       if (best < 0) break;
@@ -217,6 +231,7 @@ struct Worker {
       Node &n = g.arena[p.path[i]];
       n.visits += 1;
       n.value_sum += std::fabs(cc == n.color ? value : 1.0 - value);
+      g.refresh(p.path[i]);
     }
     ++st.playouts;
     return true;
@@ -226,6 +241,9 @@ struct Worker {
     g.arena.clear();
     g.arena.reserve(1 << 14);
     g.arena.emplace_back();
+    g.stat.clear();
+    g.stat.reserve(1 << 14);
+    g.stat.emplace_back();
     g.arena[0].color = g.pos.side;
     g.launched = g.done = 0;
   }
@@ -259,7 +277,9 @@ struct Worker {
       }
       if (!parked.empty()) {
         long n_eval = 0;
+        const auto tf = std::chrono::steady_clock::now();
         if (cab_leafq_flush(q, &n_eval) != CAB_OK) { std::fprintf(stderr, "%s\n", cab_last_error()); std::exit(1); }
+        st.flush_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tf).count();
         const double *res = nullptr;
         cab_leafq_results(q, &res);
         ++st.flushes;
@@ -267,7 +287,7 @@ struct Worker {
         st.max_flush = std::max(st.max_flush, n_eval);
         for (auto &p : parked) {
           GameState &g = games[p.game];
-          for (int i = 0; i < p.path_len; ++i) { g.arena[p.path[i]].visits -= 1; g.arena[p.path[i]].vloss -= 1; }
+          for (int i = 0; i < p.path_len; ++i) { Node &v = g.arena[p.path[i]]; v.visits -= 1; v.vloss -= 1; g.refresh(p.path[i]); }
           finish_expansion(p, res);
         }
         still.clear();
@@ -287,7 +307,7 @@ struct Worker {
           double max_score = -1.0;
           const double pf = puct_parent(root);
           for (int i = 0; i < root.n_children; ++i) {
-            const double s = puct(pf, g.arena[root.first_child + i]);
+            const double s = puct(pf, g.stat[root.first_child + i]);
             if (s > max_score) { max_score = s; best = root.first_child + i; }
           }
           if (best >= 0) play(g.pos, g.arena[best].move);
@@ -354,6 +374,7 @@ int main(int argc, char **argv) {
   for (auto &w : workers) {
     tot.playouts += w.st.playouts; tot.boards += w.st.boards; tot.flushes += w.st.flushes;
     tot.expansions += w.st.expansions; tot.moves += w.st.moves; tot.max_flush = std::max(tot.max_flush, w.st.max_flush);
+    tot.flush_seconds += w.st.flush_seconds;
   }
   long n_cases = 0;
   if (cases_path)
@@ -366,10 +387,10 @@ int main(int argc, char **argv) {
   std::printf("{\"config\": \"MCTS self-play, virtual-loss leaf batching\", \"games\": %d, \"playouts_per_move\": %d, \"moves_per_game\": %d, "
               "\"threads\": %d, \"in_flight_per_thread\": %d, \"network_priors\": %d, \"seconds\": %.3f, \"moves_played\": %ld, "
               "\"playouts\": %ld, \"playouts_per_s\": %.1f, \"boards_evaluated\": %ld, \"boards_per_s\": %.1f, \"expansions\": %ld, "
-              "\"flushes\": %ld, \"avg_boards_per_flush\": %.1f, \"max_boards_per_flush\": %ld, \"gpu_launches\": %ld, \"cases_written\": %ld}\n",
+              "\"flushes\": %ld, \"avg_boards_per_flush\": %.1f, \"max_boards_per_flush\": %ld, \"gpu_launches\": %ld, \"cases_written\": %ld, \"gpu_wait_fraction\": %.3f}\n",
               games, playouts, moves, threads, in_flight, (int) network_priors, secs, tot.moves, tot.playouts, tot.playouts / secs,
               tot.boards, tot.boards / secs, tot.expansions, tot.flushes, tot.flushes ? (double) tot.boards / tot.flushes : 0.0,
-              tot.max_flush, launches, n_cases);
+              tot.max_flush, launches, n_cases, tot.flush_seconds / (secs * threads));
   cab_net_destroy(net);
   return 0;
 }
