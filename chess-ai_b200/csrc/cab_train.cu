@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <atomic>
 #include <cstring>
 
 #include "cab_internal.cuh"
@@ -228,10 +229,10 @@ static int launch_backward(cab_net *net, const double *d_targets, long b0, long 
   a.err_sum = net->d_grad + net->n_weights;  // [sumE, sumE', count, spare]
   const size_t smem = forward_smem_bytes(a.a_units, geo.n_cons, geo.n_stages, net->stage_bytes);
   const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * geo.ctas_per_sm);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_devices{0};   // the attribute is per device: one bit per device ordinal
+  if (!(attr_devices.load() >> (net->device & 63) & 1)) {
     CAB_CUDA(cudaFuncSetAttribute(mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_devices.fetch_or(1ull << (net->device & 63));
   }
   mlp_backward_kernel<<<grid, geo.n_cons * 64, smem, stream>>>(a);
   net->launches++;
@@ -257,10 +258,10 @@ static int launch_grad(cab_net *net, long n, cudaStream_t stream) {
   a.psis = net->d_psis;
   a.save_stride = net->train_cap * 8;
   a.grad = net->d_grad;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_devices{0};
+  if (!(attr_devices.load() >> (net->device & 63) & 1)) {
     CAB_CUDA(cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_devices.fetch_or(1ull << (net->device & 63));
   }
   a.next_item = reinterpret_cast<int *>(net->d_scalars + 16);
   CAB_CUDA(cudaMemsetAsync(a.next_item, 0, sizeof(int), stream));
