@@ -171,7 +171,7 @@ struct ForwardArgs {
 __host__ __device__ inline size_t fwd_smem_ring(int n_stages, int stage_bytes) { return (size_t) n_stages * stage_bytes; }
 __host__ __device__ inline size_t fwd_smem_abuf(int n_pairs, int a_units) { return (size_t) n_pairs * a_units * kUnitBytes; }
 __host__ __device__ inline size_t fwd_smem_tail(int n_stages) {
-  return (size_t) kSmemChunks * sizeof(ChunkDesc) + 32 * sizeof(double) + (size_t) n_stages * (sizeof(uint64_t) + sizeof(uint32_t)) + 16;
+  return (size_t) kSmemChunks * sizeof(ChunkDesc) + kExpTblSize * sizeof(double) + (size_t) n_stages * (sizeof(uint64_t) + sizeof(uint32_t)) + 16;
 }
 
 #define CAB_PROF_T(var) long long var = 0; if (PROF) var = clock64();
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
   uint8_t *ring = smem;
   double2 *abuf_all = reinterpret_cast<double2 *>(smem + fwd_smem_ring(n_stages, stage_bytes));
   ChunkDesc *s_chunks = reinterpret_cast<ChunkDesc *>(smem + fwd_smem_ring(n_stages, stage_bytes) + fwd_smem_abuf(n_pairs, args.a_units));
-  double *exp_tbl = reinterpret_cast<double *>(s_chunks + kSmemChunks);  // 2^(j/32) for the table-driven exp
-  uint64_t *full = reinterpret_cast<uint64_t *>(exp_tbl + 32);
+  double *exp_tbl = reinterpret_cast<double *>(s_chunks + kSmemChunks);  // 2^(j/256) for the table-driven exp
+  uint64_t *full = reinterpret_cast<uint64_t *>(exp_tbl + kExpTblSize);
   uint32_t *done = reinterpret_cast<uint32_t *>(full + n_stages);  // arrivals per ring slot, monotonically increasing
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
     for (int i = threadIdx.x; i < n16; i += blockDim.x)
       reinterpret_cast<int4 *>(s_chunks)[i] = reinterpret_cast<const int4 *>(args.chunks)[i];
   }
-  if (threadIdx.x >= 32 && threadIdx.x < 64) exp_tbl[threadIdx.x - 32] = c_exp2_tbl[threadIdx.x - 32];
+  for (int i = threadIdx.x; i < kExpTblSize; i += blockDim.x) exp_tbl[i] = c_exp2_tbl[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], 1);
