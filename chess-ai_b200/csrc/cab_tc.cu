@@ -101,6 +101,9 @@ static int tc_prepare(cab_net *net, long n, cudaStream_t stream) {
     CAB_CUDA(cudaFuncSetAttribute(tc::tc_gemm_bf16_kernel<tc::kEpiAct>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc::kSmemTc));
     CAB_CUDA(cudaFuncSetAttribute(tc::tc_gemm_bf16_kernel<tc::kEpiDeriv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc::kSmemTc));
     CAB_CUDA(cudaFuncSetAttribute(tc::tc_gemm_bf16_kernel<tc::kEpiGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc::kSmemTc));
+    CAB_CUDA(cudaFuncSetAttribute(tc::tc_gemm2_bf16_kernel<tc::kEpiAct>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc::kSmemTc2));
+    CAB_CUDA(cudaFuncSetAttribute(tc::tc_gemm2_bf16_kernel<tc::kEpiDeriv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc::kSmemTc2));
+    CAB_CUDA(cudaFuncSetAttribute(tc::tc_gemm2_bf16_kernel<tc::kEpiGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc::kSmemTc2));
   }
   if (stream == nullptr) stream = s->stream;  // host entry point: everything on the state's own stream
   if (!s->packed || net->tc_dirty) {
@@ -129,7 +132,27 @@ static int tc_prepare(cab_net *net, long n, cudaStream_t stream) {
   return CAB_OK;
 }
 
-static int launch_gemm(cab_net *net, int epi, const CUtensorMap &ma, const CUtensorMap &mb, const tc::TcGemmArgs &a, cudaStream_t stream) {
+// CTA-pair kernels (cta_group::2, 256 x 256 tiles) pay off once there are several waves of pair-sized work items:
+// measured forward 1.18 vs 1.14 PFLOP/s at 16 384 boards, 1.14 vs 1.08 at 65 536, but 0.84 vs 0.94 at 4 096.
+// CAB_TC_PAIR=0 / 1 forces one kind.
+static bool use_pair(long n_boards) {
+  static const int forced = getenv("CAB_TC_PAIR") ? atoi(getenv("CAB_TC_PAIR")) : -1;
+  return forced >= 0 ? forced != 0 : n_boards >= 12288;
+}
+static int b_box_rows(bool pair) { return pair ? tc::BN / 2 : tc::BN; }
+
+static int launch_gemm(cab_net *net, int epi, const CUtensorMap &ma, const CUtensorMap &mb, const tc::TcGemmArgs &a, cudaStream_t stream,
+                       bool pair) {
+  if (pair) {
+    const int items = ((a.M + 2 * tc::BM - 1) / (2 * tc::BM)) * (a.N / tc::BN) * std::max(1, a.split_k);
+    const int grid = 2 * std::min(items, net->sm_count / 2);
+    if (epi == tc::kEpiAct) tc::tc_gemm2_bf16_kernel<tc::kEpiAct><<<grid, tc::kThreadsTc, tc::kSmemTc2, stream>>>(ma, mb, a);
+    else if (epi == tc::kEpiDeriv) tc::tc_gemm2_bf16_kernel<tc::kEpiDeriv><<<grid, tc::kThreadsTc, tc::kSmemTc2, stream>>>(ma, mb, a);
+    else tc::tc_gemm2_bf16_kernel<tc::kEpiGrad><<<grid, tc::kThreadsTc, tc::kSmemTc2, stream>>>(ma, mb, a);
+    net->launches++;
+    CAB_CUDA(cudaGetLastError());
+    return CAB_OK;
+  }
   const int tiles = ((a.M + tc::BM - 1) / tc::BM) * (a.N / tc::BN);
   const int grid = std::min(tiles * std::max(1, a.split_k), net->sm_count);
   if (epi == tc::kEpiAct) tc::tc_gemm_bf16_kernel<tc::kEpiAct><<<grid, tc::kThreadsTc, tc::kSmemTc, stream>>>(ma, mb, a);
@@ -155,12 +178,13 @@ static int tc_forward(cab_net *net, const int8_t *d_codes, long n, double *d_out
     net->launches++;
   }
   int cur = 0;
+  const bool pair = use_pair(n);
   const __nv_bfloat16 *in = x0;
   for (int l = 0; l + 2 < L; ++l) {
     const int K = net->dims[l], N = net->dims[l + 1];
     CUtensorMap mx, mw;
     if ((rc = make_map(&mx, in, n, K, tc::BM)) != CAB_OK) return rc;
-    if ((rc = make_map(&mw, s->wt[l], N, K, tc::BN)) != CAB_OK) return rc;
+    if ((rc = make_map(&mw, s->wt[l], N, K, b_box_rows(pair))) != CAB_OK) return rc;
     tc::TcGemmArgs a{};
     a.M = (int) n; a.N = N; a.K = K;
     a.Y = save ? s->a_rm[l + 1] : s->act[1 - cur];
@@ -168,7 +192,7 @@ static int tc_forward(cab_net *net, const int8_t *d_codes, long n, double *d_out
     a.ldt = s->ld;
     a.split_k = 1;
     a.apply_act = 1;
-    if ((rc = launch_gemm(net, tc::kEpiAct, mx, mw, a, stream)) != CAB_OK) return rc;
+    if ((rc = launch_gemm(net, tc::kEpiAct, mx, mw, a, stream, pair)) != CAB_OK) return rc;
     in = a.Y;
     cur = 1 - cur;
   }
@@ -203,7 +227,7 @@ static int tc_train_prepare(cab_net *net, long n, cudaStream_t stream) {
       v->assign(L - 1, nullptr);
     }
     cudaFree(s->psi_out); cudaFree(s->y);
-    const long ld = (n + tc::BM - 1) / tc::BM * tc::BM;
+    const long ld = (n + 2 * tc::BM - 1) / (2 * tc::BM) * (2 * tc::BM);   // whole 256-row tiles: pad rows of the transposed copies stay inside a row
     for (int l = 0; l + 1 < L; ++l) {
       const size_t bytes = (size_t) ld * net->dims[l] * 2;
       CAB_CUDA(cudaMalloc(&s->a_rm[l], bytes));
@@ -241,31 +265,34 @@ int tc_grad(cab_net *net, const int8_t *d_codes, const double *d_targets, long n
                                                                                     s->p_rm[L - 2], s->p_t[L - 2], s->ld);
   net->launches += 3;
   CAB_CUDA(cudaGetLastError());
+  const bool pair = use_pair(n);
   for (int l = L - 3; l >= 0; --l) {
     const int K = net->dims[l], N = net->dims[l + 1];
     {  // dW_l[K][N] = a_l^T psi_{l+1}: contraction over boards, both operands read from their transposed copies
       CUtensorMap ma, mb;
       if ((rc = make_map(&ma, s->a_t[l], K, n, tc::BM, s->ld)) != CAB_OK) return rc;
-      if ((rc = make_map(&mb, s->p_t[l + 1], N, n, tc::BN, s->ld)) != CAB_OK) return rc;
+      if ((rc = make_map(&mb, s->p_t[l + 1], N, n, b_box_rows(pair), s->ld)) != CAB_OK) return rc;
       tc::TcGemmArgs a{};
       a.M = K; a.N = N; a.K = (int) n;
       a.G = d_grad + net->woff[l];
-      const int tiles = ((K + tc::BM - 1) / tc::BM) * (N / tc::BN);
+      const int tile_rows = pair ? 2 * tc::BM : tc::BM;
+      const int tiles = ((K + tile_rows - 1) / tile_rows) * (N / tc::BN);
       const int kblocks = (int) ((n + tc::BK - 1) / tc::BK);
       // narrow layers (the 64-wide input) have too few output tiles to fill the chip: split the board dimension
-      a.split_k = tiles * 2 > net->sm_count ? 1 : std::max(1, std::min(kblocks / 8, net->sm_count / tiles));
-      if ((rc = launch_gemm(net, tc::kEpiGrad, ma, mb, a, stream)) != CAB_OK) return rc;
+      const int slots = pair ? net->sm_count / 2 : net->sm_count;   // concurrently running work items
+      a.split_k = tiles * 2 > slots ? 1 : std::max(1, std::min(kblocks / 8, slots / tiles));
+      if ((rc = launch_gemm(net, tc::kEpiGrad, ma, mb, a, stream, pair)) != CAB_OK) return rc;
     }
     if (l >= 1) {  // psi_l = (psi_{l+1} W_l^T) * f'(a_l); the input layer needs no psi (network.cpp:248: L stops at 0)
       CUtensorMap ma, mb;
       if ((rc = make_map(&ma, s->p_rm[l + 1], n, N, tc::BM)) != CAB_OK) return rc;
-      if ((rc = make_map(&mb, s->wkn[l], K, N, tc::BN)) != CAB_OK) return rc;
+      if ((rc = make_map(&mb, s->wkn[l], K, N, b_box_rows(pair))) != CAB_OK) return rc;
       tc::TcGemmArgs a{};
       a.M = (int) n; a.N = K; a.K = N;
       a.Y = s->p_rm[l]; a.Yt = s->p_t[l]; a.ldt = s->ld;
       a.aux = s->a_rm[l];
       a.split_k = 1;
-      if ((rc = launch_gemm(net, tc::kEpiDeriv, ma, mb, a, stream)) != CAB_OK) return rc;
+      if ((rc = launch_gemm(net, tc::kEpiDeriv, ma, mb, a, stream, pair)) != CAB_OK) return rc;
     }
   }
   return CAB_OK;

@@ -106,6 +106,80 @@ struct TcGemmArgs {
   int apply_act;             // kEpiAct: 0 = plain product
 };
 
+// One 32-column chunk of one accumulator row (r[] = the thread's 32 fp32 values from TMEM) through the epilogue EPI.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const TcGemmArgs &args, const uint32_t (&r)[32], int row, size_t row_off, int nb, int c,
+                                               int n_splits, int lane) {
+  if (EPI == kEpiGrad) {
+    if (row < args.M) {
+      double *g = args.G + row_off + c;
+      if (n_splits == 1) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          *reinterpret_cast<double2 *>(g + i) = make_double2((double) __uint_as_float(r[i]), (double) __uint_as_float(r[i + 1]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          asm volatile("red.global.add.f64 [%0], %1;" ::"l"(g + i), "d"((double) __uint_as_float(r[i])) : "memory");
+      }
+    }
+  } else {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (EPI == kEpiAct) {
+      if (args.apply_act) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = act_f32(v[i]);
+      }
+    } else {
+      uint4 a4[4] = {};
+      if (row < args.M) {
+        const uint4 *ap = reinterpret_cast<const uint4 *>(args.aux + row_off + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a4[i] = __ldg(ap + i);
+      }
+      const __nv_bfloat162 *ab = reinterpret_cast<const __nv_bfloat162 *>(a4);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 a = __bfloat1622float2(ab[i]);
+        v[2 * i] *= 1.0f - 0.0625f * a.x * a.x;
+        v[2 * i + 1] *= 1.0f - 0.0625f * a.y * a.y;
+      }
+    }
+    if (row >= args.M) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.0f;  // pad rows of the transposed copy stay zero
+    }
+    if (row < args.M) {
+      uint4 *dst = reinterpret_cast<uint4 *>(args.Y + row_off + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t *>(&b);
+        }
+        dst[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+    if (args.Yt != nullptr && row < args.ldt) {   // warp-uniform: a warp holds 32 consecutive rows and ldt is a multiple of 256
+      // transposed copy: lanes are consecutive rows; lane pairs swap so that each lane stores two rows of one
+      // column as one 4-byte word -> every column receives 64 contiguous bytes from the warp
+      __nv_bfloat16 *tcol = args.Yt + (size_t) (nb * BN + c) * args.ldt + (row & ~1);
+      const bool odd = lane & 1;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float send = odd ? v[i] : v[i + 1];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        const __nv_bfloat162 b = odd ? __floats2bfloat162_rn(recv, v[i + 1]) : __floats2bfloat162_rn(v[i], recv);
+        *reinterpret_cast<__nv_bfloat162 *>(tcol + (size_t) (i + (odd ? 1 : 0)) * args.ldt) = b;
+      }
+    }
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const TcGemmArgs args) {
@@ -198,74 +272,7 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (as * BN + c), r);
-        if (EPI == kEpiGrad) {
-          if (row < args.M) {
-            double *g = args.G + row_off + c;
-            if (n_splits == 1) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 2)
-                *reinterpret_cast<double2 *>(g + i) = make_double2((double) __uint_as_float(r[i]), (double) __uint_as_float(r[i + 1]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                asm volatile("red.global.add.f64 [%0], %1;" ::"l"(g + i), "d"((double) __uint_as_float(r[i])) : "memory");
-            }
-          }
-        } else {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (EPI == kEpiAct) {
-            if (args.apply_act) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = act_f32(v[i]);
-            }
-          } else {
-            uint4 a4[4] = {};
-            if (row < args.M) {
-              const uint4 *ap = reinterpret_cast<const uint4 *>(args.aux + row_off + c);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) a4[i] = __ldg(ap + i);
-            }
-            const __nv_bfloat162 *ab = reinterpret_cast<const __nv_bfloat162 *>(a4);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 a = __bfloat1622float2(ab[i]);
-              v[2 * i] *= 1.0f - 0.0625f * a.x * a.x;
-              v[2 * i + 1] *= 1.0f - 0.0625f * a.y * a.y;
-            }
-          }
-          if (row >= args.M) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.0f;  // pad rows of the transposed copy stay zero
-          }
-          if (row < args.M) {
-            uint4 *dst = reinterpret_cast<uint4 *>(args.Y + row_off + c);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t *>(&b);
-              }
-              dst[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          }
-          if (args.Yt != nullptr) {
-            // transposed copy: lanes are consecutive rows; lane pairs swap so that each lane stores two rows of one
-            // column as one 4-byte word -> every column receives 64 contiguous bytes from the warp
-            __nv_bfloat16 *tcol = args.Yt + (size_t) (nb * BN + c) * args.ldt + (row & ~1);
-            const bool odd = lane & 1;
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float send = odd ? v[i] : v[i + 1];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-              const __nv_bfloat162 b = odd ? __floats2bfloat162_rn(recv, v[i + 1]) : __floats2bfloat162_rn(v[i], recv);
-              *reinterpret_cast<__nv_bfloat162 *>(tcol + (size_t) (i + (odd ? 1 : 0)) * args.ldt) = b;
-            }
-          }
-        }
+        epilogue_chunk<EPI>(args, r, row, row_off, nb, c, n_splits, lane);
       }
       tmem_fence_before();
       __syncwarp();
@@ -279,6 +286,172 @@ tc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   if (warp == 2) {
     tmem_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-PAIR variant (cta_group::2): two CTAs of one cluster (the two SMs of a TPC) compute a 256 x 256 output tile.
+// Each CTA stages ITS 128 rows of A and ITS 128 of the 256 B rows (32 KB per k-block instead of 48 KB: the single-CTA
+// kernel needs ~64 B/clk/SM from L2 at full tensor rate, more than L2 delivers to 148 SMs at once), the leader CTA
+// issues one tcgen05.mma.cta_group::2 with M = 256 that reads both CTAs' shared memory and writes each CTA's half of
+// the accumulator into that CTA's own TMEM; every CTA runs its own epilogue on its 128 rows.
+//   full[s]        waited by the leader's MMA warp only; BOTH CTAs' TMA loads complete_tx on the LEADER's barrier
+//                  (barrier address with the peer bit cleared), the leader expects the bytes of both
+//   empty[s]       per CTA; the leader's tcgen05.commit multicasts the arrival to both CTAs
+//   tmem_full[a]   per CTA, same multicast commit
+//   tmem_empty[a]  the leader's; 8 arrivals = the 4 epilogue warps of each CTA (the peer's arrive through mapa)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStagesTc2 = 6;
+constexpr uint32_t kBytesA2 = BM * BK * 2, kBytesB2 = (BN / 2) * BK * 2;
+constexpr size_t kSmemTc2 = (size_t) kStagesTc2 * (kBytesA2 + kBytesB2) + 1024 + 256;
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) ((2 * BM) >> 4) << 24);
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address inside a CTA pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const void *tmap, int c0, int c1, uint64_t *leader_bar_local) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(leader_bar_local) & kPeerBitMask), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {   // arrives on the same barrier offset in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t) 3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar_local) {   // arrive on CTA 0's copy of this barrier
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar_local))
+      : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTc, 1)
+tc_gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const TcGemmArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+  uint8_t *smem_a = smem;
+  uint8_t *smem_b = smem + (size_t) kStagesTc2 * kBytesA2;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t) kStagesTc2 * (kBytesA2 + kBytesB2));
+  uint64_t *empty = full + kStagesTc2;
+  uint64_t *tmem_full = empty + kStagesTc2;
+  uint64_t *tmem_empty = tmem_full + kAccumStages;
+  uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + kAccumStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_blocks_n = args.N / BN, n_blocks_m = (args.M + 2 * BM - 1) / (2 * BM);   // 256-row blocks
+  const int n_kblocks = (args.K + BK - 1) / BK;
+  const int kb_per_item = (n_kblocks + args.split_k - 1) / args.split_k;
+  const int n_splits = (n_kblocks + kb_per_item - 1) / kb_per_item;
+  const int n_items = n_blocks_m * n_blocks_n * n_splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStagesTc2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < kAccumStages; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tmem_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers exist before anybody signals across the pair
+  tmem_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------- TMA producer (both CTAs) -------------------------------
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int item = pair_id; item < n_items; item += n_pairs) {
+        const int tile = item / n_splits, split = item % n_splits;
+        const int mb = tile / n_blocks_n, nb = tile % n_blocks_n;
+        const int kb0 = split * kb_per_item, kb1 = min(kb0 + kb_per_item, n_kblocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * (kBytesA2 + kBytesB2));
+          tma_load_2d_pair(smem_a + (size_t) s * kBytesA2, &tmap_x, kb * BK, mb * 2 * BM + (int) rank * BM, &full[s]);
+          tma_load_2d_pair(smem_b + (size_t) s * kBytesB2, &tmap_w, kb * BK, nb * BN + (int) rank * (BN / 2), &full[s]);
+          if (++s == kStagesTc2) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------- MMA issuer (leader CTA only) ---------------------------
+    uint32_t s = 0, ph = 0, as = 0, aph = 0;
+    for (int item = pair_id; item < n_items; item += n_pairs) {
+      const int split = item % n_splits;
+      const int kb0 = split * kb_per_item, kb1 = min(kb0 + kb_per_item, n_kblocks);
+      mbar_wait(&tmem_empty[as], aph ^ 1);          // both CTAs' epilogues drained this accumulator
+      tmem_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t) as * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[s], ph);                    // both CTAs' bytes landed
+        tmem_fence_after();
+        if (lane == 0) {
+          const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + (size_t) s * kBytesA2));
+          const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + (size_t) s * kBytesB2));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_pair(tmem_d, a_desc + (uint64_t) (k * 2), b_desc + (uint64_t) (k * 2), kIdesc2, (kb != kb0 || k != 0) ? 1u : 0u);
+          umma_commit_pair(&empty[s]);              // frees the stage in both CTAs
+          if (kb == kb1 - 1) umma_commit_pair(&tmem_full[as]);
+        }
+        __syncwarp();
+        if (++s == kStagesTc2) { s = 0; ph ^= 1; }
+      }
+      if (++as == kAccumStages) { as = 0; aph ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------- epilogue (both CTAs, own 128 rows) ---------------------
+    const int q = warp & 3;
+    uint32_t as = 0, aph = 0;
+    for (int item = pair_id; item < n_items; item += n_pairs) {
+      const int tile = item / n_splits;
+      const int mb = tile / n_blocks_n, nb = tile % n_blocks_n;
+      mbar_wait(&tmem_full[as], aph);
+      tmem_fence_after();
+      const int row = mb * 2 * BM + (int) rank * BM + q * 32 + lane;
+      const size_t row_off = (size_t) row * args.N + (size_t) nb * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (as * BN + c), r);
+        epilogue_chunk<EPI>(args, r, row, row_off, nb, c, n_splits, lane);
+      }
+      tmem_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+      if (++as == kAccumStages) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tmem_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's shared memory and barriers stay alive until the leader is done with them
+  if (warp == 2) {
+    tmem_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
   }
 }
 

@@ -125,3 +125,22 @@ def test_bf16_trainer_refuses_the_default_net(cab, golden):
     net = cab.Network.from_weights([64, 144, 225, 100, 1], golden["latest_weights"])
     with pytest.raises(cab.CabError):
         cab.Optimizer.train_batch_bf16(net, golden["syn_codes"][:64], np.zeros(64), 2.0)
+
+
+def test_cta_pair_kernel_matches_single_cta(tmp_path):
+    """The cta_group::2 GEMM (default from 12 288 boards up) against the single-CTA one on the same ragged problem."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for mode in ("0", "1"):
+        path = str(tmp_path / ("r%s.npz" % mode))
+        env = dict(os.environ, CAB_TC_PAIR=mode)
+        subprocess.run([sys.executable, os.path.join(root, "tests", "tc_pair_worker.py"), path], check=True, env=env, timeout=300)
+        out[mode] = np.load(path)
+    a, b = out["0"], out["1"]
+    assert np.all(np.isfinite(b["y"])) and np.abs(a["y"] - b["y"]).max() < 1e-6           # same products, same k order
+    assert np.array_equal(a["stats"][1:2], b["stats"][1:2]) and abs(a["stats"][2] - b["stats"][2]) < 1e-9
+    dw_a, dw_b = a["w_after"] - a["w_before"], b["w_after"] - b["w_before"]
+    assert np.linalg.norm(dw_b) > 0 and np.linalg.norm(dw_a - dw_b) <= 1e-5 * np.linalg.norm(dw_a)
