@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libchessai_b200.so")
 SOURCES = ["cab_api.cu", "cab_train.cu", "cab_tc.cu", "cab_leafq.cu"]
-HEADERS = ["cab_internal.cuh", "mlp_stream_kernel.cuh", "train_kernels.cuh", os.path.join("..", "..", "include", "chessai_b200.h")]
+HEADERS = ["cab_internal.cuh", "mlp_stream_kernel.cuh", "tc_gemm_bf16.cuh", "train_kernels.cuh", os.path.join("..", "..", "include", "chessai_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -61,10 +61,11 @@ def build(verbose=False, force=False):
     if force or _stale(tr, tr_deps):
         subprocess.check_call([gxx, "-std=c++17", "-O2", "-static-libstdc++", "-static-libgcc", "-o", tr, tr_deps[0],
                                "-L" + LIB_DIR, "-lchessai_b200", "-Wl,-rpath,$ORIGIN"])
-    tool = os.path.join(LIB_DIR, "pipe_peaks")
-    tsrc = os.path.join(CSRC, "tools", "pipe_peaks.cu")
-    if force or _stale(tool, [tsrc]):
-        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-w", tsrc, "-o", tool])
+    for name in ("pipe_peaks", "tma_stream"):      # microbenchmarks behind the roofline denominators / design choices
+        tool = os.path.join(LIB_DIR, name)
+        tsrc = os.path.join(CSRC, "tools", name + ".cu")
+        if force or _stale(tool, [tsrc]):
+            subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-w", tsrc, "-o", tool])
     return LIB
 
 
