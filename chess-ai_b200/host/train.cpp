@@ -9,8 +9,15 @@
 // Beyond the reference: lambda, the step count and the generation number persist in <out_dir>/trainer_state.txt, so a
 // restarted trainer continues instead of starting again at lambda0 and overwriting gen-0 (the reference loses both).
 //
-//   train <net_in.txt> <shard> <out_dir> <exact|batch> <steps> <batch> [device] [seed] [save_every]
-// Prints one JSON object. No CPU fallback.
+// Data-parallel (batch mode): one process per GPU; rank r trains on cases r, r + world, r + 2 world, ... of the shard,
+// the library all-reduces the gradient (cab_dp_init: NCCL), every rank takes the identical decision and applies the
+// identical update; rank 0 alone writes checkpoints. Rendezvous without MPI: rank 0 writes the 128-byte NCCL id to
+// <id_file>, the others poll for it.
+//
+//   train <net_in.txt> <shard> <out_dir> <exact|batch> <steps> <batch> [device] [seed] [save_every] [rank world id_file]
+// Prints one JSON object (rank 0). No CPU fallback.
+#include <unistd.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -73,14 +80,42 @@ int main(int argc, char **argv) {
   const int device = argc > 7 ? std::atoi(argv[7]) : 0;
   const unsigned long long seed = argc > 8 ? std::strtoull(argv[8], nullptr, 10) : 5489;
   const long save_every = argc > 9 ? std::atol(argv[9]) : 20;   // GAMES_PER_NETWORK_SAVE default, initialization.h:56
+  const int rank = argc > 12 ? std::atoi(argv[10]) : 0, world = argc > 12 ? std::atoi(argv[11]) : 1;
+  const std::string id_file = argc > 12 ? argv[12] : "";
+  if (world > 1 && mode != "batch") { std::fprintf(stderr, "data-parallel training needs batch mode\n"); return 2; }
   if ((mode != "exact" && mode != "batch") || steps <= 0 || batch <= 0 || save_every <= 0) { std::fprintf(stderr, "bad arguments\n"); return 2; }
 
   std::vector<cases::Case> cs;
   if (!cases::read_shard(shard, cs) || cs.empty()) { std::fprintf(stderr, "cannot read shard %s\n", shard.c_str()); return 1; }
+  if (world > 1) {                              // this rank's stride of the shard
+    std::vector<cases::Case> mine;
+    for (size_t i = (size_t) rank; i < cs.size(); i += (size_t) world) mine.push_back(cs[i]);
+    cs.swap(mine);
+    if (cs.empty()) { std::fprintf(stderr, "shard smaller than the world size\n"); return 1; }
+  }
   TrainerState st;
   const bool resumed = load_state(out_dir + "/trainer_state.txt", st);
   cab_net *net = nullptr;
   CK(cab_net_load_text(resumed ? (out_dir + "/latest.txt").c_str() : net_in.c_str(), device, &net));
+  if (world > 1) {
+    unsigned char id[128];
+    if (rank == 0) {
+      CK(cab_dp_unique_id(id));
+      const std::string tmp = id_file + ".tmp";
+      FILE *f = std::fopen(tmp.c_str(), "wb");
+      if (!f || std::fwrite(id, 1, 128, f) != 128 || std::fclose(f) != 0 || std::rename(tmp.c_str(), id_file.c_str()) != 0) {
+        std::fprintf(stderr, "cannot write %s\n", id_file.c_str());
+        return 1;
+      }
+    } else {
+      FILE *f = nullptr;
+      for (int tries = 0; tries < 600 && !(f = std::fopen(id_file.c_str(), "rb")); ++tries) usleep(100000);
+      if (!f || std::fread(id, 1, 128, f) != 128) { std::fprintf(stderr, "cannot read %s\n", id_file.c_str()); return 1; }
+      std::fclose(f);
+    }
+    CK(cab_dp_init(net, id, rank, world));
+  }
+  const bool writer = rank == 0;                // only rank 0 touches the checkpoint directory
 
   std::mt19937_64 rng(seed + (unsigned long long) st.steps);
   std::vector<int8_t> codes((size_t) std::max(batch, save_every) * 64);
@@ -106,7 +141,7 @@ int main(int argc, char **argv) {
       for (long i = 0; i < n; ++i) accepted += acc[(size_t) i];
       decisions += n; samples += n; done += n;
       st.steps += n; st.resets += resets;
-      if (n == save_every) CK(rotate(net, out_dir, st));
+      if (writer && n == save_every) CK(rotate(net, out_dir, st));
     }
   } else {
     for (long s = 0; s < steps; ++s) {
@@ -122,19 +157,20 @@ int main(int argc, char **argv) {
         CK(cab_dropout(net, 0.01, seed, (uint64_t) st.resets, nullptr));
         ++st.resets;
       }
-      if (st.steps % save_every == 0) CK(rotate(net, out_dir, st));
+      if (writer && st.steps % save_every == 0) CK(rotate(net, out_dir, st));
     }
   }
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  CK(rotate(net, out_dir, st));                 // NetworkStorage::flushStorage, network.cpp:366-370
+  if (writer) CK(rotate(net, out_dir, st));     // NetworkStorage::flushStorage, network.cpp:366-370
   long launches = 0;
   cab_net_launch_count(net, &launches);
-  std::printf("{\"config\": \"trainer over packed case shards\", \"mode\": \"%s\", \"cases_in_shard\": %zu, \"steps\": %ld, \"batch\": %ld, "
+  if (world > 1) CK(cab_dp_shutdown(net));
+  if (writer) std::printf("{\"config\": \"trainer over packed case shards\", \"mode\": \"%s\", \"cases_in_shard\": %zu, \"steps\": %ld, \"batch\": %ld, "
               "\"resumed\": %s, \"seconds\": %.3f, \"samples\": %ld, \"samples_per_s\": %.1f, \"accepted\": %ld, \"decisions\": %ld, "
               "\"first_err\": %.9e, \"last_err\": %.9e, \"lambda\": %.17e, \"resets\": %ld, \"generations_written\": %ld, "
-              "\"total_steps\": %ld, \"gpu_launches\": %ld}\n",
-              mode.c_str(), cs.size(), steps, batch, resumed ? "true" : "false", secs, samples, samples / secs, accepted, decisions,
-              first_err, last_err, st.lambda, st.resets - resets0, st.generation - gen0, st.steps, launches);
+              "\"total_steps\": %ld, \"gpu_launches\": %ld, \"world\": %d}\n",
+              mode.c_str(), cs.size(), steps, batch, resumed ? "true" : "false", secs, samples * world, samples * world / secs, accepted, decisions,
+              first_err, last_err, st.lambda, st.resets - resets0, st.generation - gen0, st.steps, launches, world);
   cab_net_destroy(net);
   return 0;
 }

@@ -1,4 +1,5 @@
 """The N > 1 path: world_size-2 gloo test of the host-side logic on CPU, and a 2-GPU NCCL test (skipped with < 2 GPUs)."""
+import importlib
 import json
 import os
 import subprocess
@@ -48,3 +49,40 @@ def test_nccl_world2_training_matches_single_gpu(cab, tmp_path):
         assert (lam, acc) == (lam_s, acc_s)
         assert abs(e0 - e0_s) <= 1e-10 * abs(e0_s) and abs(e1 - e1_s) <= 1e-8 * abs(e1_s)
     assert r[0]["max_abs_w_diff_vs_single"] < 1e-10
+
+
+@pytest.mark.gpu
+def test_cpp_trainer_data_parallel_world2_matches_replicas(cab, tmp_path):
+    """chess-ai_b200/lib/train in data-parallel mode: two processes, two GPUs, file rendezvous of the NCCL id;
+    steps are accepted, only rank 0 reports and writes the checkpoint."""
+    import json
+    import subprocess
+    if cab.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "chess-ai_b200", "lib", "train")
+    synth = importlib.import_module("chess-ai_b200.synth")
+    codes = synth.synthetic_boards(512, seed=77)
+    teacher = cab.Network.from_weights([64, 144, 225, 100, 1], np.fromfile(os.path.join(root, "tests", "golden", "latest_weights.f64"), dtype="<f8"))
+    targets = teacher.predict_batch(codes)
+    rec = np.zeros(len(codes), dtype=np.dtype([("codes", "i1", 64), ("target", "<f8")]))
+    rec["codes"], rec["target"] = codes, targets
+    shard = str(tmp_path / "c.shard")
+    rec.tofile(shard)
+    start = str(tmp_path / "start.txt")
+    student = cab.Network.randomNetwork([64, 144, 225, 100, 1], seed=21)
+    student.set_weights(student.get_weights() * 0.1)
+    student.dump(start)
+    out = str(tmp_path / "dump")
+    os.makedirs(out)
+    idf = str(tmp_path / "nccl.id")
+    procs = [subprocess.Popen([exe, start, shard, out, "batch", "80", "64", str(r), "5", "100", str(r), "2", idf], stdout=subprocess.PIPE)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs)
+    r = json.loads(outs[0].strip().splitlines()[-1])
+    assert r["world"] == 2 and r["samples"] == 80 * 64 * 2 and r["accepted"] > 0, r     # (errors are per drawn batch: not comparable)
+    assert outs[1].strip() == ""                                     # only rank 0 reports and writes
+    assert sorted(os.listdir(out)) == ["latest.txt", "trainer_state.txt"]
+    w_dp = cab.Network.loadFromFile(os.path.join(out, "latest.txt")).get_weights()
+    assert np.all(np.isfinite(w_dp)) and np.abs(w_dp - student.get_weights()).max() > 0
