@@ -82,6 +82,8 @@ _SIGS = {
     "cab_dp_init": [_vp, _vp, C.c_int, C.c_int],
     "cab_dp_shutdown": [_vp],
     "cab_grad_buffer": [_vp, C.POINTER(_vp), _lp],
+    "cab_eval_f16_dev": [_vp, _vp, C.c_long, _vp, _vp],
+    "cab_eval_f16_host": [_vp, _i8p, C.c_long, _f64p],
     "cab_train_batch_bf16_host": [_vp, _i8p, _f64p, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp],
     "cab_train_batch_bf16_dev": [_vp, _vp, _vp, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp, _vp],
     "cab_grad_bf16_dev": [_vp, _vp, _vp, C.c_long, _vp],
@@ -331,6 +333,16 @@ class Network:
         out = np.zeros(len(c), dtype=np.float64)
         _ck(lib().cab_eval_bf16_host(self._h, c.reshape(-1), len(c), out))
         return out
+
+    def predict_batch_f16(self, codes):
+        """Reduced-precision fused tcgen05 evaluation (fp16 operands) of a {64, N1, N2, N3, 1} net. Not a parity path."""
+        c = _as_codes(codes)
+        out = np.empty(len(c), dtype=np.float64)
+        _ck(lib().cab_eval_f16_host(self._h, c.reshape(-1), len(c), out))
+        return out
+
+    def eval_f16_dev_ptr(self, codes_dev_ptr, n, out_dev_ptr, stream=0):
+        _ck(lib().cab_eval_f16_dev(self._h, codes_dev_ptr, n, out_dev_ptr, stream))
 
     def eval_bf16_dev_ptr(self, codes_dev_ptr, n, out_dev_ptr, stream=0):
         _ck(lib().cab_eval_bf16_dev(self._h, codes_dev_ptr, n, out_dev_ptr, stream))

@@ -393,7 +393,7 @@ static int create_exact(const std::vector<int> &dims, int device, cab_net **out)
   net->fp64_ok = consumer_warps_for(std::max(net->fwd.a_units, net->bwd.a_units), net->stage_bytes) > 0;
   CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  net->pack_dirty = net->tc_dirty = true;
+  net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   *out = net;
   return CAB_OK;
 }
@@ -551,7 +551,7 @@ int cab_net_set_weights(cab_net *net, const double *w, long n) {
   if (rc != CAB_OK) return rc;
   CAB_CUDA(cudaDeviceSynchronize());
   CAB_CUDA(cudaMemcpy(net->d_w, w, n * sizeof(double), cudaMemcpyHostToDevice));
-  net->pack_dirty = net->tc_dirty = true;
+  net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   return CAB_OK;
 }
 
@@ -573,7 +573,7 @@ int cab_net_randomize(cab_net *net, uint64_t seed, uint64_t stream) {
   net->launches++;
   CAB_CUDA(cudaGetLastError());
   CAB_CUDA(cudaDeviceSynchronize());
-  net->pack_dirty = net->tc_dirty = true;
+  net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   return CAB_OK;
 }
 
@@ -583,7 +583,7 @@ int cab_net_zero(cab_net *net) {
   if (rc != CAB_OK) return rc;
   CAB_CUDA(cudaDeviceSynchronize());
   CAB_CUDA(cudaMemset(net->d_w, 0, net->n_weights * sizeof(double)));
-  net->pack_dirty = net->tc_dirty = true;
+  net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   return CAB_OK;
 }
 

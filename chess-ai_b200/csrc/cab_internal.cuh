@@ -92,6 +92,8 @@ struct cab_net {
   bool pack_dirty = true;    // packed streams stale w.r.t. d_w
   bool fp64_ok = true;       // the fp64 stream kernels fit this network's widest layer in shared memory
   bool tc_dirty = true;      // bf16 copies of the tcgen05 path stale w.r.t. d_w
+  bool f16_dirty = true;     // fp16 shared-memory image of the fused tcgen05 path stale w.r.t. d_w
+  void *f16 = nullptr;       // F16State of cab_tc.cu
   void *tc = nullptr;        // cab::TcState of the bf16 tcgen05 path (cab_tc.cu), created on first use
   cab::StreamPlan fwd, bwd;
   // saved-activation geometry (units per board-group, per layer)

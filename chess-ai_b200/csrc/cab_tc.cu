@@ -5,6 +5,7 @@
 
 #include "cab_internal.cuh"
 #include "tc_gemm_bf16.cuh"
+#include "mlp_tc_fused.cuh"
 
 namespace cab {
 
@@ -64,7 +65,94 @@ static bool tc_supported(const cab_net *net) {
   return true;
 }
 
+// ---- fused fp16 path for {64, N1, N2, N3, 1} nets (mlp_tc_fused.cuh) -------------------------------------------------
+struct F16State {
+  uint8_t *image = nullptr;
+  tcf::PackArgs pack{};
+  tcf::FusedArgs args{};
+  size_t smem = 0;
+  int8_t *d_codes = nullptr;
+  double *d_out = nullptr;
+  long cap = 0;
+  cudaStream_t stream = nullptr;
+};
+
+static bool f16_supported(const cab_net *net) {
+  if (net->dims.size() != 5 || net->dims[0] != 64 || net->dims[4] != 1) return false;
+  for (int l = 1; l <= 3; ++l)
+    if (net->dims[l] < 1 || net->dims[l] > 256) return false;
+  return true;
+}
+
+static void f16_free(cab_net *net) {
+  F16State *s = static_cast<F16State *>(net->f16);
+  if (!s) return;
+  cudaFree(s->image); cudaFree(s->d_codes); cudaFree(s->d_out);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  net->f16 = nullptr;
+}
+
+static int f16_prepare(cab_net *net, cudaStream_t stream) {
+  if (!f16_supported(net)) {
+    set_error("the fused fp16 path needs a net shaped {64, N1, N2, N3, 1} with N1, N2, N3 <= 256");
+    return CAB_EINVAL;
+  }
+  F16State *s = static_cast<F16State *>(net->f16);
+  if (!s) {
+    s = new F16State();
+    net->f16 = s;
+    uint32_t off = 0;
+    for (int l = 0; l < 3; ++l) {
+      const int K = net->dims[l], N = net->dims[l + 1];
+      const int kp = l == 0 ? 64 : (s->pack.n_pad[l - 1] + 63) / 64 * 64;   // next K = previous padded width, in 64-blocks
+      const int np = (N + 15) / 16 * 16;
+      s->pack.K[l] = K; s->pack.N[l] = N; s->pack.woff[l] = net->woff[l];
+      s->pack.k_pad[l] = kp; s->pack.n_pad[l] = np; s->pack.w_off[l] = off;
+      s->args.k_pad[l] = kp; s->args.n_pad[l] = np; s->args.w_off[l] = off;
+      off += (uint32_t) np * (uint32_t) kp * 2u;     // np multiple of 8 and kp of 64: every K block is a whole number of 1 KB atoms
+    }
+    s->pack.K[3] = net->dims[3]; s->pack.N[3] = 1; s->pack.woff[3] = net->woff[3];
+    s->pack.w_last_off = s->args.w_last_off = off;
+    off += (uint32_t) s->pack.n_pad[2] * 4u;
+    off = (off + 15u) & ~15u;
+    s->args.image_bytes = off;
+    s->smem = (size_t) off + 1024 + 64;
+    if (s->smem > 227 * 1024) { set_error("the fp16 weight image (%u bytes) does not fit shared memory", off); return CAB_EINVAL; }
+    CAB_CUDA(cudaMalloc(&s->image, off));
+    s->pack.image = s->image;
+    s->args.image = s->image;
+    CAB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CAB_CUDA(cudaFuncSetAttribute(tcf::mlp_tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem));
+  }
+  if (net->f16_dirty) {
+    s->pack.w = net->d_w;
+    tcf::f16_pack_kernel<<<64, 256, 0, stream ? stream : s->stream>>>(s->pack);
+    net->launches++;
+    CAB_CUDA(cudaGetLastError());
+    CAB_CUDA(cudaStreamSynchronize(stream ? stream : s->stream));   // rare (weights changed); later launches may use other streams
+    net->f16_dirty = false;
+  }
+  return CAB_OK;
+}
+
+static int f16_forward(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream) {
+  int rc = f16_prepare(net, stream);
+  if (rc != CAB_OK) return rc;
+  F16State *s = static_cast<F16State *>(net->f16);
+  tcf::FusedArgs a = s->args;
+  a.codes = d_codes;
+  a.n_boards = n;
+  a.out = d_out;
+  const long tiles = (n + tcf::kTile - 1) / tcf::kTile;
+  tcf::mlp_tc_fused_kernel<<<(int) std::min<long>(tiles, net->sm_count), tcf::kThreads, s->smem, stream ? stream : s->stream>>>(a);
+  net->launches++;
+  CAB_CUDA(cudaGetLastError());
+  return CAB_OK;
+}
+
 void tc_free(cab_net *net) {
+  f16_free(net);
   TcState *s = static_cast<TcState *>(net->tc);
   if (!s) return;
   for (auto *p : s->wt) cudaFree(p);
@@ -315,6 +403,36 @@ int cab_eval_bf16_dev(cab_net *net, const int8_t *codes_dev, long n, double *out
   if (n == 0) return CAB_OK;
   CAB_CUDA(cudaSetDevice(net->device));
   return tc_forward(net, codes_dev, n, out_dev, (cudaStream_t) stream);
+}
+
+int cab_eval_f16_dev(cab_net *net, const int8_t *codes_dev, long n, double *out_dev, void *stream) {
+  if (!net || n < 0 || (n > 0 && (!codes_dev || !out_dev))) { set_error("bad argument"); return CAB_EINVAL; }
+  if (n == 0) return CAB_OK;
+  CAB_CUDA(cudaSetDevice(net->device));
+  return f16_forward(net, codes_dev, n, out_dev, (cudaStream_t) stream);
+}
+
+int cab_eval_f16_host(cab_net *net, const int8_t *codes, long n, double *out) {
+  if (!net || n < 0 || (n > 0 && (!codes || !out))) { set_error("bad argument"); return CAB_EINVAL; }
+  if (n == 0) return CAB_OK;
+  CAB_CUDA(cudaSetDevice(net->device));
+  int rc = f16_prepare(net, nullptr);
+  if (rc != CAB_OK) return rc;
+  F16State *s = static_cast<F16State *>(net->f16);
+  std::lock_guard<std::mutex> lk(net->mu);      // the staging buffers are per net
+  if (n > s->cap) {
+    cudaFree(s->d_codes); cudaFree(s->d_out);
+    s->d_codes = nullptr; s->d_out = nullptr;
+    CAB_CUDA(cudaMalloc(&s->d_codes, n * 64));
+    CAB_CUDA(cudaMalloc(&s->d_out, n * sizeof(double)));
+    s->cap = n;
+  }
+  CAB_CUDA(cudaMemcpyAsync(s->d_codes, codes, n * 64, cudaMemcpyHostToDevice, s->stream));
+  rc = f16_forward(net, s->d_codes, n, s->d_out, s->stream);
+  if (rc != CAB_OK) return rc;
+  CAB_CUDA(cudaMemcpyAsync(out, s->d_out, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CAB_CUDA(cudaStreamSynchronize(s->stream));
+  return CAB_OK;
 }
 
 int cab_eval_bf16_host(cab_net *net, const int8_t *codes, long n, double *out) {

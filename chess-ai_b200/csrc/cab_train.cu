@@ -347,7 +347,7 @@ static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d
   }
   apply_update_kernel<<<(int) std::min<long>((nw + 255) / 256, 148L * 8), 256, 0, stream>>>(net->d_w, net->d_dw, net->d_grad, nw, *lambda);
   net->launches += 2;
-  net->pack_dirty = net->tc_dirty = true;
+  net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   // re-forward (network.cpp:265) and E'
   if (bf16) {
     if ((rc = tc_forward_out(net, d_codes, n, d_tout, stream)) != CAB_OK) return rc;
@@ -381,7 +381,7 @@ static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d
     *lambda /= rate;                                          // :273
     rollback_kernel<<<(int) std::min<long>((nw + 255) / 256, 148L * 8), 256, 0, stream>>>(net->d_w, net->d_dw, nw);
     net->launches++;
-    net->pack_dirty = net->tc_dirty = true;
+    net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
     CAB_CUDA(cudaGetLastError());
   }
   if (accepted) *accepted = ok ? 1 : 0;
@@ -438,7 +438,7 @@ static int train_sequence_impl(cab_net *net, const int8_t *codes, const double *
   if (resets) memcpy(resets, &h[1], sizeof(int));
   if (err) *err = h[2];
   if (new_err) *new_err = h[3];
-  net->pack_dirty = net->tc_dirty = true;
+  net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   return CAB_OK;
 }
 
@@ -463,7 +463,7 @@ int cab_dropout(cab_net *net, double rate, uint64_t seed, uint64_t offset, long 
   CAB_CUDA(cudaMemcpy(&h, d_hits, sizeof h, cudaMemcpyDeviceToHost));
   cudaFree(d_hits);
   if (hits) *hits = (long) h;
-  net->pack_dirty = net->tc_dirty = true;
+  net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   return CAB_OK;
 }
 

@@ -118,6 +118,13 @@ CAB_API int cab_prior_softmax_host(int device, const double *logits, const int *
  * identical sign of the evaluation away from |y| < 0.15 (tests/test_tc_gpu.py). */
 CAB_API int cab_eval_bf16_dev(cab_net *net, const int8_t *codes_dev, long n_boards, double *out_dev, void *stream);
 CAB_API int cab_eval_bf16_host(cab_net *net, const int8_t *codes_host, long n_boards, double *out_host);
+/* Optional REDUCED-PRECISION fast path for nets shaped {64, N1, N2, N3, 1}, N1..N3 <= 256 (the default network):
+ * Network::predictPosition as ONE tcgen05 kernel, fp16 operands, fp32 accumulation, weights resident in shared
+ * memory, activations kept in tensor memory between the layers. NOT a parity path. Stated tolerance vs the fp64 path:
+ * |dy| <= 0.05 on the (-4, 4) output scale for weights U(-1,1)/sqrt(fan_in) and identical sign wherever |y| >= 0.05;
+ * for the shipped, saturated latest.txt: the same sign on >= 99.5 % of synthetic boards (tests/test_tc_gpu.py). */
+CAB_API int cab_eval_f16_dev(cab_net *net, const int8_t *codes_dev, long n_boards, double *out_dev, void *stream);
+CAB_API int cab_eval_f16_host(cab_net *net, const int8_t *codes_host, long n_boards, double *out_host);
 
 /* ---- training (network::Optimizer  network.cpp:223-292, train loop main/network/train.cpp:39-68) ---------------- */
 /* Optimizer::optimize on ONE case: forward, backprop with in-place update (step lambda), re-forward, accept

@@ -144,3 +144,46 @@ def test_cta_pair_kernel_matches_single_cta(tmp_path):
     assert np.array_equal(a["stats"][1:2], b["stats"][1:2]) and abs(a["stats"][2] - b["stats"][2]) < 1e-9
     dw_a, dw_b = a["w_after"] - a["w_before"], b["w_after"] - b["w_before"]
     assert np.linalg.norm(dw_b) > 0 and np.linalg.norm(dw_a - dw_b) <= 1e-5 * np.linalg.norm(dw_a)
+
+
+# ---- fused fp16 tcgen05 path for {64, N1, N2, N3, 1} nets (cab_eval_f16_*, csrc/mlp_tc_fused.cuh) --------------------
+# Stated tolerance (fp16 operands, fp32 accumulation, hardware tanh): |dy| <= 0.05 on the (-4, 4) scale for weights
+# U(-1,1)/sqrt(fan_in) and identical sign wherever |y| >= 0.05. Not a parity path.
+F16_ATOL = 0.05
+
+
+@pytest.mark.parametrize("dims,n", [([64, 144, 225, 100, 1], 1000), ([64, 16, 16, 16, 1], 300), ([64, 192, 128, 256, 1], 515),
+                                    ([64, 100, 37, 200, 1], 129), ([64, 144, 225, 100, 1], 1)])
+def test_fused_f16_forward_vs_fp64_path(cab, golden, dims, n):
+    w = scaled_weights(dims, sum(dims) + 7)
+    net = cab.Network.from_weights(dims, w)
+    codes = np.ascontiguousarray(np.tile(golden["syn_codes"], (2, 1))[:n])
+    want = net.predict_batch(codes)
+    got = net.predict_batch_f16(codes)
+    assert np.all(np.isfinite(got))
+    assert np.abs(got - want).max() < F16_ATOL, np.abs(got - want).max()
+    strong = np.abs(want) >= F16_ATOL
+    assert np.array_equal(np.sign(got[strong]), np.sign(want[strong]))
+
+
+def test_fused_f16_on_the_shipped_saturated_net(cab, golden):
+    net = cab.Network.from_weights([64, 144, 225, 100, 1], golden["latest_weights"])
+    codes = golden["syn_codes"][:2048]
+    want, got = net.predict_batch(codes), net.predict_batch_f16(codes)
+    strong = np.abs(want) >= 0.15
+    agree = (np.sign(got[strong]) == np.sign(want[strong])).mean()
+    assert strong.sum() > 1500 and agree >= 0.995, agree
+    assert np.corrcoef(got, want)[0, 1] > 0.99
+
+
+def test_fused_f16_tracks_weight_updates_and_refuses_other_shapes(cab, golden):
+    dims = [64, 144, 225, 100, 1]
+    net = cab.Network.from_weights(dims, scaled_weights(dims, 1))
+    codes = golden["syn_codes"][:256]
+    a = net.predict_batch_f16(codes)
+    net.set_weights(scaled_weights(dims, 2))
+    b = net.predict_batch_f16(codes)
+    assert np.abs(b - net.predict_batch(codes)).max() < F16_ATOL and np.abs(a - b).max() > 0.2
+    wide = cab.Network.from_weights([64, 512, 1], scaled_weights([64, 512, 1], 3))
+    with pytest.raises(cab.CabError):
+        wide.predict_batch_f16(codes)
