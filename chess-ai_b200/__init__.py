@@ -84,6 +84,7 @@ _SIGS = {
     "cab_grad_buffer": [_vp, C.POINTER(_vp), _lp],
     "cab_eval_f16_dev": [_vp, _vp, C.c_long, _vp, _vp],
     "cab_eval_f16_host": [_vp, _i8p, C.c_long, _f64p],
+    "cab_eval_f16_dev_batches": [_vp, _vp, C.c_long, C.c_long, _vp, C.POINTER(_vp), C.c_int],
     "cab_train_batch_bf16_host": [_vp, _i8p, _f64p, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp],
     "cab_train_batch_bf16_dev": [_vp, _vp, _vp, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp, _vp],
     "cab_grad_bf16_dev": [_vp, _vp, _vp, C.c_long, _vp],
@@ -343,6 +344,10 @@ class Network:
 
     def eval_f16_dev_ptr(self, codes_dev_ptr, n, out_dev_ptr, stream=0):
         _ck(lib().cab_eval_f16_dev(self._h, codes_dev_ptr, n, out_dev_ptr, stream))
+
+    def eval_f16_dev_batches(self, codes_dev_ptr, n, batch, out_dev_ptr, streams):
+        arr = (_vp * len(streams))(*streams)
+        _ck(lib().cab_eval_f16_dev_batches(self._h, codes_dev_ptr, n, batch, out_dev_ptr, arr, len(streams)))
 
     def eval_bf16_dev_ptr(self, codes_dev_ptr, n, out_dev_ptr, stream=0):
         _ck(lib().cab_eval_bf16_dev(self._h, codes_dev_ptr, n, out_dev_ptr, stream))

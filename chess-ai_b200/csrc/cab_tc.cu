@@ -117,7 +117,7 @@ static int f16_prepare(cab_net *net, cudaStream_t stream) {
     off += (uint32_t) s->pack.n_pad[2] * 4u;
     off = (off + 15u) & ~15u;
     s->args.image_bytes = off;
-    s->smem = (size_t) off + 1024 + 64;
+    s->smem = (size_t) off + 1024 + 64 + tcf::kTile * sizeof(float);   // image, alignment slack, barriers, partial dot products
     if (s->smem > 227 * 1024) { set_error("the fp16 weight image (%u bytes) does not fit shared memory", off); return CAB_EINVAL; }
     CAB_CUDA(cudaMalloc(&s->image, off));
     s->pack.image = s->image;
@@ -410,6 +410,20 @@ int cab_eval_f16_dev(cab_net *net, const int8_t *codes_dev, long n, double *out_
   if (n == 0) return CAB_OK;
   CAB_CUDA(cudaSetDevice(net->device));
   return f16_forward(net, codes_dev, n, out_dev, (cudaStream_t) stream);
+}
+
+int cab_eval_f16_dev_batches(cab_net *net, const int8_t *codes_dev, long n, long batch, double *out_dev, void *const *streams,
+                             int n_streams) {
+  if (!net || n < 0 || batch <= 0 || n_streams <= 0 || !streams || (n > 0 && (!codes_dev || !out_dev))) { set_error("bad argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  int rc = f16_prepare(net, (cudaStream_t) streams[0]);     // weights packed (and that stream drained) before any launch
+  if (rc != CAB_OK) return rc;
+  int i = 0;
+  for (long b0 = 0; b0 < n; b0 += batch, ++i) {
+    rc = f16_forward(net, codes_dev + b0 * 64, std::min(batch, n - b0), out_dev + b0, (cudaStream_t) streams[i % n_streams]);
+    if (rc != CAB_OK) return rc;
+  }
+  return CAB_OK;
 }
 
 int cab_eval_f16_host(cab_net *net, const int8_t *codes, long n, double *out) {

@@ -3,7 +3,8 @@
 // BASELINE.json's north_star for nets shaped {64, N1, N2, N3, 1} with N1, N2, N3 <= 256 (the default 64-144-225-100-1).
 // Not a parity path: see cab_eval_f16_* in include/chessai_b200.h for the stated tolerance.
 //
-// One CTA per SM, persistent over tiles of 128 boards; thread t of the CTA owns board t of the tile = TMEM lane t.
+// One CTA per SM, persistent over tiles of 128 boards; TMEM lane t = board t of the tile. Two threads serve a lane
+// (warps w and w + 4 both reach lane quarter w % 4): they split the 16-column chunks of every epilogue between them.
 //   * ALL weights live in shared memory for the whole kernel (fp16, zero-padded, pre-swizzled by f16_pack_kernel into
 //     the K-major SWIZZLE_128B image tcgen05 reads through shared-memory descriptors): 167 KB for the default net,
 //     fetched once per CTA with TMA bulk copies
@@ -23,7 +24,7 @@ namespace cab {
 namespace tcf {
 
 constexpr int kTile = 128;               // boards per tile = TMEM lanes
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 constexpr int kColA = 0, kColD = 128;    // TMEM column bases
 constexpr int kTmemCols = 512;
 constexpr int kMaxLayers = 3;            // tensor-core layers (the 4th, N = 1, is a dot product)
@@ -77,7 +78,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_fused_kernel(const FusedAr
   uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem + args.image_bytes);   // weights landed
   uint64_t *bar_mma = bar_w + 1;                                             // a layer's MMAs retired
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
+  float *dot_half = reinterpret_cast<float *>(tmem_slot + 4);                // [128] partial dot products of the upper half
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3, half = warp >> 2, row_in_tile = quarter * 32 + lane;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
@@ -97,20 +100,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_fused_kernel(const FusedAr
   __syncthreads();
   tc::tmem_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_base = tmem_base + ((uint32_t) (warp * 32) << 16);   // this warp's TMEM lane quarter
+  const uint32_t lane_base = tmem_base + ((uint32_t) (quarter * 32) << 16);   // this warp's TMEM lane quarter
   const float *w_last = reinterpret_cast<const float *>(smem + args.w_last_off);
   mbar_wait(bar_w, 0);
 
   uint32_t mma_phase = 0;
   const long n_tiles = (args.n_boards + kTile - 1) / kTile;
   for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long board = tile * kTile + threadIdx.x;
+    const long board = tile * kTile + row_in_tile;
     const bool valid = board < args.n_boards;
     // ---- Network::loadBoard: 64 codes -> fp16 k * 0.4 -> this lane's A row, K = 64 = 32 columns ----
     {
       const uint4 *src = reinterpret_cast<const uint4 *>(args.codes + (valid ? board : 0) * 64);
 #pragma unroll
-      for (int part = 0; part < 4; ++part) {
+      for (int part = 2 * half; part < 2 * half + 2; ++part) {
         uint4 raw = valid ? __ldg(src + part) : make_uint4(0, 0, 0, 0);
         const int8_t *c = reinterpret_cast<const int8_t *>(&raw);
         uint32_t packed[8];
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_fused_kernel(const FusedAr
       if (l + 1 < kMaxLayers) {
         // f() on this board's row, packed to fp16, stored back as the next layer's A row
 #pragma unroll 1
-        for (int c = 0; c < np; c += 16) {
+        for (int c = 16 * half; c < np; c += 32) {
           uint32_t r[16], packed[8];
           tmem_ld16(lane_base + kColD + c, r);
 #pragma unroll
@@ -151,12 +154,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_fused_kernel(const FusedAr
           tmem_st8(lane_base + kColA + c / 2, packed);
         }
         const uint32_t zeros[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // K padding of the next layer must be finite: zero it
-        for (int c = np / 2; c < args.k_pad[l + 1] / 2; c += 8) tmem_st8(lane_base + kColA + c, zeros);
+        if (half == 0)
+          for (int c = np / 2; c < args.k_pad[l + 1] / 2; c += 8) tmem_st8(lane_base + kColA + c, zeros);
         tmem_wait_st();
       } else {
         // last hidden layer: keep fp32 and fold the N = 1 output layer in as a dot product
 #pragma unroll 1
-        for (int c = 0; c < np; c += 16) {
+        for (int c = 16 * half; c < np; c += 32) {
           uint32_t r[16];
           tmem_ld16(lane_base + kColD + c, r);
 #pragma unroll
@@ -164,9 +168,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_fused_kernel(const FusedAr
         }
       }
     }
-    if (valid) args.out[board] = (double) tc::act_f32(dot);
+    if (half == 1) dot_half[row_in_tile] = dot;
     tc::tmem_fence_before();
     __syncthreads();                                 // the accumulator has been read: the next tile may overwrite it
+    if (half == 0 && valid) args.out[board] = (double) tc::act_f32(dot + dot_half[row_in_tile]);
   }
 
   tc::tmem_fence_before();

@@ -125,6 +125,9 @@ CAB_API int cab_eval_bf16_host(cab_net *net, const int8_t *codes_host, long n_bo
  * for the shipped, saturated latest.txt: the same sign on >= 99.5 % of synthetic boards (tests/test_tc_gpu.py). */
 CAB_API int cab_eval_f16_dev(cab_net *net, const int8_t *codes_dev, long n_boards, double *out_dev, void *stream);
 CAB_API int cab_eval_f16_host(cab_net *net, const int8_t *codes_host, long n_boards, double *out_host);
+/* n boards as launches of `batch`, round-robin over the caller's streams (like cab_eval_dev_batches) */
+CAB_API int cab_eval_f16_dev_batches(cab_net *net, const int8_t *codes_dev, long n_boards, long batch, double *out_dev,
+                             void *const *streams, int n_streams);
 
 /* ---- training (network::Optimizer  network.cpp:223-292, train loop main/network/train.cpp:39-68) ---------------- */
 /* Optimizer::optimize on ONE case: forward, backprop with in-place update (step lambda), re-forward, accept
