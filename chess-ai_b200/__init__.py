@@ -65,6 +65,7 @@ _SIGS = {
     "cab_leafq_destroy": [_vp],
     "cab_leafq_push": [_vp, _i8p, C.c_long, _lp],
     "cab_leafq_pending": [_vp, _lp],
+    "cab_leafq_set_precision": [_vp, C.c_int],
     "cab_leafq_flush": [_vp, _lp],
     "cab_leafq_results": [_vp, C.POINTER(_dp)],
     "cab_leafq_stats": [_vp, _lp, _lp, _lp],

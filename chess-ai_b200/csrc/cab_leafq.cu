@@ -16,6 +16,9 @@ namespace cab {
 int ensure_packed(cab_net *net, cudaStream_t stream);
 int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d_out, double *d_save, long save_stride,
                    cudaStream_t stream);
+}  // namespace cab
+extern "C" int cab_eval_f16_dev(cab_net *net, const int8_t *codes_dev, long n, double *out_dev, void *stream);
+namespace cab {
 
 // one warp per segment (node); segments are short (a chess position has ~20-40 children)
 __global__ void __launch_bounds__(256) prior_softmax_kernel(const double *__restrict__ logits, const int *__restrict__ seg_off,
@@ -44,6 +47,7 @@ struct cab_leafq {
   std::vector<cudaEvent_t> events;
   std::atomic<long> head{0};
   long launches = 0, flushes = 0, evaluated = 0;
+  bool f16 = false;            // evaluate with the reduced-precision fused tcgen05 kernel (cab_leafq_set_precision)
 };
 
 using namespace cab;
@@ -108,6 +112,30 @@ int cab_leafq_flush(cab_leafq *q, long *n_evaluated) {
   if (n == 0) return CAB_OK;
   cab_net *net = q->net;
   CAB_CUDA(cudaSetDevice(net->device));
+  if (q->f16) {           // reduced precision: one fused launch per stream piece
+    const long piece = (n + q->n_streams - 1) / q->n_streams;
+    int i = 0;
+    for (long b0 = 0; b0 < n; b0 += piece, ++i) {
+      const long nb = std::min(piece, n - b0);
+      cudaStream_t s = q->streams[i];
+      CAB_CUDA(cudaMemcpyAsync(q->d_codes + b0 * 64, q->h_codes + b0 * 64, nb * 64, cudaMemcpyHostToDevice, s));
+      int rc;
+      if (net->f16 == nullptr || net->f16_dirty) {   // the fp16 weight image is (re)built under the net's lock (rare)
+        std::lock_guard<std::mutex> lk(net->mu);
+        rc = cab_eval_f16_dev(net, q->d_codes + b0 * 64, nb, q->d_out + b0, s);
+      } else {
+        rc = cab_eval_f16_dev(net, q->d_codes + b0 * 64, nb, q->d_out + b0, s);
+      }
+      if (rc != CAB_OK) return rc;
+      CAB_CUDA(cudaMemcpyAsync(q->h_out + b0, q->d_out + b0, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+      ++q->launches;
+    }
+    for (auto s : q->streams) CAB_CUDA(cudaStreamSynchronize(s));
+    ++q->flushes;
+    q->evaluated += n;
+    q->head.store(0);
+    return CAB_OK;
+  }
   if (net->pack_dirty) {  // weights changed since the last evaluation (rare): re-pack once, under the net's lock
     std::lock_guard<std::mutex> lk(net->mu);
     int rc = ensure_packed(net, q->streams[0]);
@@ -128,6 +156,14 @@ int cab_leafq_flush(cab_leafq *q, long *n_evaluated) {
   ++q->flushes;
   q->evaluated += n;
   q->head.store(0);
+  return CAB_OK;
+}
+
+// precision = 0: the fp64 reference-precision kernel (default); 1: the fused fp16 tcgen05 kernel (cab_eval_f16_*: nets
+// shaped {64, N1, N2, N3, 1} only, reduced precision, no parity claim)
+int cab_leafq_set_precision(cab_leafq *q, int precision) {
+  if (!q || (precision != 0 && precision != 1)) { set_error("bad argument"); return CAB_EINVAL; }
+  q->f16 = precision == 1;
   return CAB_OK;
 }
 

@@ -19,7 +19,8 @@
 // target 10*(4*b + result)/5 and is appended to the packed shard `cases_path`.
 //
 //   selfplay <latest.txt> <games> <playouts_per_move> <moves_per_game> <threads> <in_flight_per_thread> <network_priors>
-//            [device] [seed] [cases_path] [save_ratio]
+//            [device] [seed] [cases_path] [save_ratio] [precision: fp64 | f16]
+// (cases_path "-" = none; precision f16 = the reduced-precision fused tcgen05 evaluator, see cab_leafq_set_precision)
 // Prints one JSON object. No CPU fallback: needs libchessai_b200.so and a GPU.
 #include <atomic>
 #include <chrono>
@@ -92,6 +93,7 @@ struct Worker {
   int playouts_per_move, moves_per_game, in_flight;
   bool network_priors;
   double save_ratio = 0.0;
+  int precision = 0;
   std::vector<cases::Case> finished_cases;
   std::mt19937_64 rng;
   Stats st;
@@ -249,7 +251,10 @@ struct Worker {
   }
 
   void run() {
-    if (cab_leafq_create(net, 1 << 18, 4096, 2, &q) != CAB_OK) { std::fprintf(stderr, "%s\n", cab_last_error()); std::exit(1); }
+    if (cab_leafq_create(net, 1 << 18, 4096, 2, &q) != CAB_OK || cab_leafq_set_precision(q, precision) != CAB_OK) {
+      std::fprintf(stderr, "%s\n", cab_last_error());
+      std::exit(1);
+    }
     for (auto &g : games) new_root(g);
     std::vector<Playout> parked, still;
     parked.reserve(in_flight);
@@ -345,7 +350,8 @@ int main(int argc, char **argv) {
   const bool network_priors = std::atoi(argv[7]) != 0;
   const int device = argc > 8 ? std::atoi(argv[8]) : 0;
   const unsigned long long seed = argc > 9 ? std::strtoull(argv[9], nullptr, 10) : 1234;
-  const char *cases_path = argc > 10 ? argv[10] : nullptr;
+  const char *cases_path = argc > 10 && std::strcmp(argv[10], "-") != 0 ? argv[10] : nullptr;
+  const int precision = argc > 12 && std::strcmp(argv[12], "f16") == 0 ? 1 : 0;
   const double save_ratio = cases_path ? (argc > 11 ? std::atof(argv[11]) : 0.1) : 0.0;
   cab_net *net = nullptr;
   if (cab_net_load_text(argv[1], device, &net) != CAB_OK) { std::fprintf(stderr, "%s\n", cab_last_error()); return 1; }
@@ -359,6 +365,7 @@ int main(int argc, char **argv) {
     w.in_flight = in_flight;
     w.network_priors = network_priors;
     w.save_ratio = save_ratio;
+    w.precision = precision;
     w.rng.seed(seed + 7919ull * t);
     const int lo = games * t / threads, hi = games * (t + 1) / threads;
     w.games.resize(hi - lo);
@@ -387,10 +394,10 @@ int main(int argc, char **argv) {
   std::printf("{\"config\": \"MCTS self-play, virtual-loss leaf batching\", \"games\": %d, \"playouts_per_move\": %d, \"moves_per_game\": %d, "
               "\"threads\": %d, \"in_flight_per_thread\": %d, \"network_priors\": %d, \"seconds\": %.3f, \"moves_played\": %ld, "
               "\"playouts\": %ld, \"playouts_per_s\": %.1f, \"boards_evaluated\": %ld, \"boards_per_s\": %.1f, \"expansions\": %ld, "
-              "\"flushes\": %ld, \"avg_boards_per_flush\": %.1f, \"max_boards_per_flush\": %ld, \"gpu_launches\": %ld, \"cases_written\": %ld, \"gpu_wait_fraction\": %.3f}\n",
+              "\"flushes\": %ld, \"avg_boards_per_flush\": %.1f, \"max_boards_per_flush\": %ld, \"gpu_launches\": %ld, \"cases_written\": %ld, \"gpu_wait_fraction\": %.3f, \"precision\": \"%s\"}\n",
               games, playouts, moves, threads, in_flight, (int) network_priors, secs, tot.moves, tot.playouts, tot.playouts / secs,
               tot.boards, tot.boards / secs, tot.expansions, tot.flushes, tot.flushes ? (double) tot.boards / tot.flushes : 0.0,
-              tot.max_flush, launches, n_cases, tot.flush_seconds / (secs * threads));
+              tot.max_flush, launches, n_cases, tot.flush_seconds / (secs * threads), precision ? "f16" : "fp64");
   cab_net_destroy(net);
   return 0;
 }

@@ -103,6 +103,8 @@ CAB_API int cab_leafq_create(cab_net *net, long capacity, long batch, int n_stre
 CAB_API int cab_leafq_destroy(cab_leafq *q);
 CAB_API int cab_leafq_push(cab_leafq *q, const int8_t *codes, long n_boards, long *first_slot);
 CAB_API int cab_leafq_pending(cab_leafq *q, long *n_boards);
+/* 0 = fp64 reference precision (default), 1 = the fused fp16 tcgen05 kernel (reduced precision, cab_eval_f16_*) */
+CAB_API int cab_leafq_set_precision(cab_leafq *q, int precision);
 CAB_API int cab_leafq_flush(cab_leafq *q, long *n_evaluated);
 CAB_API int cab_leafq_results(cab_leafq *q, const double **results_by_slot);
 CAB_API int cab_leafq_stats(cab_leafq *q, long *launches, long *flushes, long *evaluated);

@@ -117,3 +117,28 @@ def test_selfplay_driver_on_the_fast_rules_engine(cab, golden, tmp_path):
     out0 = subprocess.check_output([exe, latest, "8", "40", "1", "2", "16", "0"], timeout=300)   # shipped inverted priors
     r0 = json.loads(out0.decode().strip().splitlines()[-1])
     assert r0["playouts"] == 8 * 40 and r0["boards_evaluated"] == r0["expansions"]               # only the parent board
+
+
+def test_leaf_queue_reduced_precision_option(cab, golden):
+    """cab_leafq_set_precision(1): the queue evaluates with the fused fp16 tcgen05 kernel (no parity claim: tolerance)."""
+    import ctypes as C
+    L = cab.lib()
+    dims = [64, 144, 225, 100, 1]
+    rng = np.random.default_rng(4)
+    w = np.concatenate([(rng.uniform(-1, 1, (k, n)) * 2.0 / np.sqrt(k)).reshape(-1) for k, n in zip(dims[:-1], dims[1:])])
+    net = cab.Network.from_weights(dims, w)
+    codes = np.ascontiguousarray(golden["syn_codes"][:1500])
+    q = C.c_void_p()
+    cab._ck(L.cab_leafq_create(net._h, 4096, 512, 2, C.byref(q)))
+    cab._ck(L.cab_leafq_set_precision(q, 1))
+    slot, n_eval, res = C.c_long(-1), C.c_long(0), C.POINTER(C.c_double)()
+    cab._ck(L.cab_leafq_push(q, codes.reshape(-1), len(codes), C.byref(slot)))
+    cab._ck(L.cab_leafq_flush(q, C.byref(n_eval)))
+    cab._ck(L.cab_leafq_results(q, C.byref(res)))
+    got = np.ctypeslib.as_array(res, shape=(len(codes),)).copy()
+    want = net.predict_batch(codes)
+    assert n_eval.value == len(codes) and slot.value == 0
+    assert np.abs(got - want).max() < 0.05
+    with pytest.raises(cab.CabError):
+        cab._ck(L.cab_leafq_set_precision(q, 7))
+    cab._ck(L.cab_leafq_destroy(q))
