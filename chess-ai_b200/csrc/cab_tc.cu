@@ -110,6 +110,7 @@ static int f16_prepare(cab_net *net, cudaStream_t stream) {
       s->pack.K[l] = K; s->pack.N[l] = N; s->pack.woff[l] = net->woff[l];
       s->pack.k_pad[l] = kp; s->pack.n_pad[l] = np; s->pack.w_off[l] = off;
       s->args.k_pad[l] = kp; s->args.n_pad[l] = np; s->args.w_off[l] = off;
+      s->args.k_steps[l] = l == 0 ? 4 : s->pack.n_pad[l - 1] / 16;   // the A row holds exactly the previous padded width
       off += (uint32_t) np * (uint32_t) kp * 2u;     // np multiple of 8 and kp of 64: every K block is a whole number of 1 KB atoms
     }
     s->pack.K[3] = net->dims[3]; s->pack.N[3] = 1; s->pack.woff[3] = net->woff[3];

@@ -34,7 +34,8 @@ struct FusedArgs {
   uint32_t image_bytes;       // multiple of 16
   uint32_t w_off[kMaxLayers]; // byte offset of each layer's image
   uint32_t w_last_off;        // byte offset of the fp32 last-layer weights (n_pad[2] floats)
-  int k_pad[kMaxLayers];      // contraction length, multiple of 64
+  int k_pad[kMaxLayers];      // contraction length of the weight image, multiple of 64 (whole swizzle atoms)
+  int k_steps[kMaxLayers];    // K steps of 16 the MMAs actually run: ceil(real K / 16)
   int n_pad[kMaxLayers];      // outputs, multiple of 16
   const int8_t *codes;        // [n_boards][64]
   long n_boards;
@@ -106,34 +107,49 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_fused_kernel(const FusedAr
 
   uint32_t mma_phase = 0;
   const long n_tiles = (args.n_boards + kTile - 1) / kTile;
+  // this thread's 32 codes of a board (its half of the 64), fetched one tile ahead: the global latency is off the path
+  auto fetch_codes = [&](long tile, uint4 &r0, uint4 &r1) {
+    const long b = tile * kTile + row_in_tile;
+    r0 = r1 = make_uint4(0, 0, 0, 0);
+    if (tile < n_tiles && b < args.n_boards) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(args.codes + b * 64) + 2 * half;
+      r0 = __ldg(src);
+      r1 = __ldg(src + 1);
+    }
+  };
+  uint4 next0, next1;
+  fetch_codes(blockIdx.x, next0, next1);
   for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long board = tile * kTile + row_in_tile;
     const bool valid = board < args.n_boards;
     // ---- Network::loadBoard: 64 codes -> fp16 k * 0.4 -> this lane's A row, K = 64 = 32 columns ----
     {
-      const uint4 *src = reinterpret_cast<const uint4 *>(args.codes + (valid ? board : 0) * 64);
+      const uint4 cur[2] = {next0, next1};
+      fetch_codes(tile + gridDim.x, next0, next1);
 #pragma unroll
-      for (int part = 2 * half; part < 2 * half + 2; ++part) {
-        uint4 raw = valid ? __ldg(src + part) : make_uint4(0, 0, 0, 0);
-        const int8_t *c = reinterpret_cast<const int8_t *>(&raw);
+      for (int p2 = 0; p2 < 2; ++p2) {
+        const uint32_t w4[4] = {cur[p2].x, cur[p2].y, cur[p2].z, cur[p2].w};
         uint32_t packed[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) packed[i] = pack_h2((float) c[2 * i] * 0.4f, (float) c[2 * i + 1] * 0.4f);
-        tmem_st8(lane_base + kColA + part * 8, packed);
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t word = w4[i >> 1] >> ((i & 1) * 16);
+          packed[i] = pack_h2((float) (int) (int8_t) (word & 0xff) * 0.4f, (float) (int) (int8_t) ((word >> 8) & 0xff) * 0.4f);
+        }
+        tmem_st8(lane_base + kColA + (2 * half + p2) * 8, packed);
       }
       tmem_wait_st();
     }
     float dot = 0.0f;
 #pragma unroll 1
     for (int l = 0; l < kMaxLayers; ++l) {
-      const int kp = args.k_pad[l], np = args.n_pad[l];
+      const int np = args.n_pad[l];
       tc::tmem_fence_before();
       __syncthreads();                               // every row of the A operand is in tensor memory
       if (threadIdx.x == 0) {
         tc::tmem_fence_after();
         const uint32_t idesc = idesc_f16(np);
         const uint32_t w_base = smem_u32(smem + args.w_off[l]);
-        for (int k = 0; k < kp / 16; ++k) {
+        for (int k = 0; k < args.k_steps[l]; ++k) {   // only the K steps that hold data: the previous width padded to 16
           // B: K block k / 4 (np rows x 128 bytes each), 32 bytes further per K step inside the swizzle atom
           const uint64_t b_desc = tc::make_smem_desc(w_base + (uint32_t) (k >> 2) * (uint32_t) np * 128u) + (uint64_t) ((k & 3) * 2);
           umma_ts(tmem_base + kColD, tmem_base + kColA + (uint32_t) k * 8u, b_desc, idesc, k != 0 ? 1u : 0u);
@@ -153,10 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_fused_kernel(const FusedAr
           for (int i = 0; i < 8; ++i) packed[i] = pack_h2(tc::act_f32(__uint_as_float(r[2 * i])), tc::act_f32(__uint_as_float(r[2 * i + 1])));
           tmem_st8(lane_base + kColA + c / 2, packed);
         }
-        const uint32_t zeros[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // K padding of the next layer must be finite: zero it
-        if (half == 0)
-          for (int c = np / 2; c < args.k_pad[l + 1] / 2; c += 8) tmem_st8(lane_base + kColA + c, zeros);
-        tmem_wait_st();
+        tmem_wait_st();                                // (n_pad is the next layer's K: no K padding left to zero)
       } else {
         // last hidden layer: keep fp32 and fold the N = 1 output layer in as a dot product
 #pragma unroll 1
