@@ -348,15 +348,18 @@ def main():
     n_fwd_launches = args.steps * (N_BOARDS // BATCH)
     avg_launch_s = (ms * 1e-3) / n_fwd_launches          # launches overlap on %d streams: region time / launches
     achieved = FLOP_PER_EVAL * BATCH / avg_launch_s * 1e-12
-    traffic = None
+    traffic = traffic_steady = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("mlp_forward_kernel_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("mlp_forward_kernel_dram_bytes_per_launch")
+            traffic_steady = tj.get("mlp_forward_kernel_dram_bytes_per_launch_steady_state")
         except Exception:
             traffic = None
     roofline = {"bound": "tensor", "pipe": "fp64 tensor pipe (DMMA.8x8x4)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_steady_state": traffic_steady,
+                "algorithmic_bytes_per_launch": 72 * BATCH,
                 "peak_source": "measured in this run with cab_measure_pipe_peak (best of 10, CUDA events); "
                                "MEASURED_PEAKS.json carries no fp64 figure",
                 "flop_per_unit": FLOP_PER_EVAL, "units_per_launch": BATCH,
