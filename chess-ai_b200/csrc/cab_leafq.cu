@@ -119,13 +119,7 @@ int cab_leafq_flush(cab_leafq *q, long *n_evaluated) {
       const long nb = std::min(piece, n - b0);
       cudaStream_t s = q->streams[i];
       CAB_CUDA(cudaMemcpyAsync(q->d_codes + b0 * 64, q->h_codes + b0 * 64, nb * 64, cudaMemcpyHostToDevice, s));
-      int rc;
-      if (net->f16 == nullptr || net->f16_dirty) {   // the fp16 weight image is (re)built under the net's lock (rare)
-        std::lock_guard<std::mutex> lk(net->mu);
-        rc = cab_eval_f16_dev(net, q->d_codes + b0 * 64, nb, q->d_out + b0, s);
-      } else {
-        rc = cab_eval_f16_dev(net, q->d_codes + b0 * 64, nb, q->d_out + b0, s);
-      }
+      const int rc = cab_eval_f16_dev(net, q->d_codes + b0 * 64, nb, q->d_out + b0, s);   // (locks only to rebuild the image)
       if (rc != CAB_OK) return rc;
       CAB_CUDA(cudaMemcpyAsync(q->h_out + b0, q->d_out + b0, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
       ++q->launches;

@@ -93,11 +93,15 @@ static void f16_free(cab_net *net) {
   net->f16 = nullptr;
 }
 
+// Builds the state / the weight image on first use and after a weight change, under the net's lock (double-checked: the
+// steady state takes no lock, so many host threads can launch concurrently).
 static int f16_prepare(cab_net *net, cudaStream_t stream) {
   if (!f16_supported(net)) {
     set_error("the fused fp16 path needs a net shaped {64, N1, N2, N3, 1} with N1, N2, N3 <= 256");
     return CAB_EINVAL;
   }
+  if (net->f16 != nullptr && !net->f16_dirty) return CAB_OK;
+  std::lock_guard<std::mutex> lk(net->mu);
   F16State *s = static_cast<F16State *>(net->f16);
   if (!s) {
     s = new F16State();
@@ -137,9 +141,8 @@ static int f16_prepare(cab_net *net, cudaStream_t stream) {
   return CAB_OK;
 }
 
-static int f16_forward(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream) {
-  int rc = f16_prepare(net, stream);
-  if (rc != CAB_OK) return rc;
+// the launch itself; the caller has run f16_prepare
+static int f16_launch(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream) {
   F16State *s = static_cast<F16State *>(net->f16);
   tcf::FusedArgs a = s->args;
   a.codes = d_codes;
@@ -150,6 +153,10 @@ static int f16_forward(cab_net *net, const int8_t *d_codes, long n, double *d_ou
   net->launches++;
   CAB_CUDA(cudaGetLastError());
   return CAB_OK;
+}
+static int f16_forward(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream) {
+  int rc = f16_prepare(net, stream);
+  return rc != CAB_OK ? rc : f16_launch(net, d_codes, n, d_out, stream);
 }
 
 void tc_free(cab_net *net) {
@@ -434,7 +441,8 @@ int cab_eval_f16_host(cab_net *net, const int8_t *codes, long n, double *out) {
   int rc = f16_prepare(net, nullptr);
   if (rc != CAB_OK) return rc;
   F16State *s = static_cast<F16State *>(net->f16);
-  std::lock_guard<std::mutex> lk(net->mu);      // the staging buffers are per net
+  static std::mutex staging_mu;                  // the staging buffers are per net; host callers take turns
+  std::lock_guard<std::mutex> lk(staging_mu);
   if (n > s->cap) {
     cudaFree(s->d_codes); cudaFree(s->d_out);
     s->d_codes = nullptr; s->d_out = nullptr;
