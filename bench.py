@@ -375,6 +375,11 @@ def main():
         cpu_baseline = {"value": rate, "unit": "evals/s", "cores": used, "kind": kind,
                         "sample": "%d of the same synthetic boards x 4 passes, one Network::clone() per thread" % CPU_SAMPLE_BOARDS,
                         "max_rel_diff_vs_gpu": agree}
+        try:  # configs[0] also asks for the single-thread rate
+            r1, _, _, _ = cpu_reference_rate(codes[:4096], 1, 1)
+            cpu_baseline["value_1_thread"] = r1
+        except Exception as exc:
+            cpu_baseline["value_1_thread_error"] = str(exc)
         try:  # Optimizer::optimize is inherently sequential per network: 1 thread
             from oracle_bind import RefOracle
             if RefOracle.available():
