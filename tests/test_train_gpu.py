@@ -6,6 +6,8 @@
   * cab_train_batch_* is the minibatch extension; its checker is oracle/mlp_oracle.c:orc_train_batch.
 Tolerances are written next to each assertion.
 """
+import importlib
+
 import numpy as np
 import pytest
 
@@ -150,3 +152,30 @@ def test_random_network_is_philox_uniform(cab, port):
         r = port.philox([i, 0, 9, 0], [1234, 0])
         u = ((int(r[3]) << 32 | int(r[2])) >> 11) / 2.0 ** 53
         assert w[i] == 2.0 * u - 1.0
+
+
+def test_full_size_batch_update_is_the_weighted_mean_of_its_halves(cab, golden):
+    """Size-independent property at the bench's batch (65 536 boards, far beyond what the CPU oracle finishes quickly):
+    dW is the batch MEAN of the per-sample updates, so for any split  n * dW(A u B) = n_A * dW(A) + n_B * dW(B),
+    and E(A u B) is the weighted mean of E(A) and E(B). Checked to rounding (fp64 sums in different orders)."""
+    synth = importlib.import_module("chess-ai_b200.synth")
+    n, n_a = 65536, 40000                                   # deliberately not aligned with the 8 192-board launch pieces
+    codes = synth.synthetic_boards(n, seed=123)
+    teacher = cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"])
+    targets = teacher.predict_batch(codes)
+    start = cab.Network.randomNetwork(DEFAULT_DIMS, seed=31)
+    w0 = start.get_weights() * 0.05
+    lam = 1e-4                                              # tiny step: accepted, so the update stays in the weights
+
+    def step(sl):
+        net = cab.Network.from_weights(DEFAULT_DIMS, w0)
+        _, acc, e0, _ = cab.Optimizer.train_batch(net, codes[sl], targets[sl], lam)
+        assert acc
+        return net.get_weights() - w0, e0
+
+    d_all, e_all = step(slice(0, n))
+    d_a, e_a = step(slice(0, n_a))
+    d_b, e_b = step(slice(n_a, n))
+    mix = (n_a * d_a + (n - n_a) * d_b) / n
+    assert np.linalg.norm(d_all) > 0 and np.linalg.norm(d_all - mix) <= 1e-9 * np.linalg.norm(d_all)
+    assert abs(e_all - (n_a * e_a + (n - n_a) * e_b) / n) <= 1e-12 * e_all
