@@ -66,6 +66,7 @@ _SIGS = {
     "cab_leafq_push": [_vp, _i8p, C.c_long, _lp],
     "cab_leafq_pending": [_vp, _lp],
     "cab_leafq_set_precision": [_vp, C.c_int],
+    "cab_prediction_host": [_vp, _i8p, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), _f64p, C.c_int, _ip],
     "cab_leafq_flush": [_vp, _lp],
     "cab_leafq_results": [_vp, C.POINTER(_dp)],
     "cab_leafq_stats": [_vp, _lp, _lp, _lp],
@@ -335,6 +336,17 @@ class Network:
         out = np.zeros(len(c), dtype=np.float64)
         _ck(lib().cab_eval_bf16_host(self._h, c.reshape(-1), len(c), out))
         return out
+
+    def prediction(self, codes, side_to_move, network_priors=False):
+        """Decider::prediction (decider.cpp:31-61): (evaluation, [((from, to), logit), ...]) in the reference's map order,
+        the position and the children that need the network evaluated in one batched launch."""
+        c = _as_codes(codes)[0]
+        ev, n = C.c_double(0), C.c_int(0)
+        moves = (C.c_int * 512)()
+        logits = np.zeros(256, dtype=np.float64)
+        _ck(lib().cab_prediction_host(self._h, c, int(side_to_move), int(bool(network_priors)), C.byref(ev), moves, logits, 256, C.byref(n)))
+        k = min(n.value, 256)
+        return ev.value, [((moves[2 * i], moves[2 * i + 1]), float(logits[i])) for i in range(k)]
 
     def predict_batch_f16(self, codes):
         """Reduced-precision fused tcgen05 evaluation (fp16 operands) of a {64, N1, N2, N3, 1} net. Not a parity path."""

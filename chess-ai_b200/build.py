@@ -10,8 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libchessai_b200.so")
-SOURCES = ["cab_api.cu", "cab_train.cu", "cab_tc.cu", "cab_leafq.cu"]
-HEADERS = ["cab_internal.cuh", "mlp_stream_kernel.cuh", "tc_gemm_bf16.cuh", "mlp_tc_fused.cuh", "train_kernels.cuh", os.path.join("..", "..", "include", "chessai_b200.h")]
+SOURCES = ["cab_api.cu", "cab_train.cu", "cab_tc.cu", "cab_leafq.cu", "cab_prediction.cu"]
+HEADERS = ["cab_internal.cuh", "mlp_stream_kernel.cuh", "tc_gemm_bf16.cuh", "mlp_tc_fused.cuh", "train_kernels.cuh", os.path.join("..", "..", "include", "chessai_b200.h"),
+           os.path.join("..", "host", "fastchess.hpp")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

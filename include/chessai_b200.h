@@ -110,6 +110,14 @@ CAB_API int cab_leafq_results(cab_leafq *q, const double **results_by_slot);
 CAB_API int cab_leafq_stats(cab_leafq *q, long *launches, long *flushes, long *evaluated);
 /* K7 — priors of expanded nodes (MCTS::expand_node, tree.cpp:299-306 + Node::expand :92): node s owns
  * logits[seg_off[s] .. seg_off[s+1]); prior_i = exp(cm_s * logit_i) / sum over the node. */
+/* Decider::prediction (decider.cpp:31-61) for a position on the network's code board (side_to_move = +1 white, -1
+ * black): *eval_out = cm * net(position); per legal move, in the reference's std::map order ((from, to) ascending, the
+ * four promotions of a pawn move sharing one key whose value is the last one assigned), moves_out[2i] = from square,
+ * moves_out[2i+1] = to square, logits_out[i] = its logit. The position and all children that need the network are
+ * evaluated in ONE batched launch. network_priors = 0: the shipped branch (cm * 20 unless the opponent has no reply,
+ * then cm * net(child)); 1: cm * net(child) for every move. *n_moves = number of keys (may exceed cap: truncated). */
+CAB_API int cab_prediction_host(cab_net *net, const int8_t *codes64, int side_to_move, int network_priors, double *eval_out,
+                        int *moves_out, double *logits_out, int cap, int *n_moves);
 CAB_API int cab_prior_softmax_host(int device, const double *logits, const int *seg_off, int n_seg, const double *color_mult,
                                    double *priors_out);
 

@@ -386,3 +386,35 @@ extern "C" int ref_save_case(const int8_t *codes, double target, const char *pat
   delete b;
   return 0;
 }
+
+// Decider::prediction (decider.cpp:31-61) on a position given as codes: the evaluation, and per legal move (in the
+// std::map's order) its from / to squares and its logit.
+extern "C" int ref_prediction_codes(void *net, const int8_t *codes, int white_to_move, double *eval_out, int *from_out, int *to_out,
+                                    double *logits_out, int cap) {
+  auto *n = static_cast<network::Network *>(net);
+  auto *g = new game::Game(8, 8);
+  std::stringstream ss;
+  ss << "8 8\n";
+  for (int i = 0; i < 64; ++i) {
+    const char *txt = piece_text(codes[i]);
+    if (txt == nullptr) { delete g; return -1; }
+    ss << i << " - " << txt << "\n";
+  }
+  game::Board *gb = g->board();
+  ss >> gb;
+  if (!white_to_move) g->_current_player_color = piece::PieceColor::BLACK;
+  g->generatePossibleMoveVectors();
+  auto pr = n->prediction(g);
+  *eval_out = pr.first;
+  int k = 0;
+  for (auto &kv : pr.second) {
+    if (k < cap) {
+      from_out[k] = kv.first.startingRow() * 8 + kv.first.startingColumn();
+      to_out[k] = kv.first.endingRow() * 8 + kv.first.endingColumn();
+      logits_out[k] = kv.second;
+    }
+    ++k;
+  }
+  delete g;
+  return k;
+}

@@ -175,3 +175,30 @@ def test_concurrent_eval_from_threads(cab, net, golden):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs
+
+
+def test_prediction_matches_the_reference_decider(cab, net, golden):
+    """cab_prediction_host = Decider::prediction (decider.cpp:31-61): golden vectors from the reference's own code
+    (tests/golden/make_prediction_golden.py) on 65 positions of recorded games, 30 of whose logits come from the
+    network (moves after which the opponent has no reply); keys in the std::map's order."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "predictions.npz"))
+    off = 0
+    n_net = 0
+    for codes, side, ev, n in zip(g["codes"], g["side"], g["eval"], g["n"]):
+        got_ev, got = net.prediction(codes, int(side))
+        want_moves, want_logits = g["moves"][off:off + n], g["logits"][off:off + n]
+        off += n
+        assert abs(got_ev - ev) <= 1e-9 * max(1e-6, abs(ev))
+        assert [m for m, _ in got] == [tuple(int(x) for x in m) for m in want_moves]
+        for (_, lg), want in zip(got, want_logits):
+            if abs(abs(want) - 20.0) < 1e-12:
+                assert lg == want
+            else:
+                n_net += 1
+                assert abs(lg - want) <= 1e-9 * max(1e-6, abs(want))
+    assert n_net == 30
+    # network-driven priors: every child evaluated, same keys
+    ev1, pri = net.prediction(g["codes"][0], int(g["side"][0]), network_priors=True)
+    ev0, bug = net.prediction(g["codes"][0], int(g["side"][0]))
+    assert ev1 == ev0 and [m for m, _ in pri] == [m for m, _ in bug] and all(abs(l) < 4.0 for _, l in pri)
