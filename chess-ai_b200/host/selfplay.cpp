@@ -140,7 +140,9 @@ struct Worker {
     for (int i = 0; i < n; ++i) {
       int8_t *dst = buf + n_boards * 64;
       std::memcpy(dst, p.pos.sq, 64);
-      apply_move(dst, mv[i]);
+      // the LOGIT of a promotion key is the one of the last promotion the reference assigns to it, the bishop's
+      // (actionMap[move] = ..., decider.cpp:52-56; cab_prediction_host); the move PLAYED stays the key's queen promotion
+      apply_move(dst, mv[i].promo != 0 ? Move{mv[i].from, mv[i].to, 7} : mv[i]);
       bool eval_child = network_priors;
       if (!eval_child) {                       // decider.cpp:52-57: the network is asked only when the opponent has no reply
         Position c;
