@@ -91,16 +91,19 @@ struct Searcher {
     cab_leafq_push(q, codes, 1, &p.pend.parent_slot);
     p.pend.moves.clear();
     p.pend.slot.clear();
-    std::map<game::Move, int> ordered;                      // std::map collapses promotions like the reference (Q8)
+    // std::map collapses the four promotions of a pawn move into the first key (the queen promotion, Q8) while
+    // actionMap[move] = ... keeps the value of the LAST one assigned (the bishop promotion), decider.cpp:52-56
+    std::map<game::Move, game::Move> ordered;
     std::vector<game::Move> moves = g->possibleMoves(col), reply;
     for (auto &m : moves) {
       if (!m.verify(board)) continue;
-      if (ordered.count(m)) continue;
-      ordered[m] = 1;
+      auto it = ordered.find(m);
+      if (it == ordered.end()) ordered.emplace(m, m);
+      else it->second = m;
     }
     for (auto &kv : ordered) {
       const game::Move &m = kv.first;
-      board->doMove(new game::Move(m), g);
+      board->doMove(new game::Move(kv.second), g);      // the board whose evaluation becomes the key's logit
       if (col.isWhite()) board->getPossibleMoves(nullptr, &reply);
       else board->getPossibleMoves(&reply, nullptr);
       long slot = -1;
