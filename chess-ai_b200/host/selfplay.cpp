@@ -19,7 +19,8 @@
 // target 10*(4*b + result)/5 and is appended to the packed shard `cases_path`.
 //
 //   selfplay <latest.txt> <games> <playouts_per_move> <moves_per_game> <threads> <in_flight_per_thread> <network_priors>
-//            [device] [seed] [cases_path] [save_ratio] [precision: fp64 | f16]
+//            [device] [seed] [cases_path] [save_ratio] [precision: fp64 | f16] [roots]
+// (roots = independent trees per move, merged like the reference's root-parallel threads; each gets playouts / roots)
 // (cases_path "-" = none; precision f16 = the reduced-precision fused tcgen05 evaluator, see cab_leafq_set_precision)
 // Prints one JSON object. No CPU fallback: needs libchessai_b200.so and a GPU.
 #include <atomic>
@@ -64,19 +65,26 @@ struct ChildStat {
 
 struct Playout {
   Position pos;
-  int game = 0, node = 0, depth = 0;
+  int tree = 0, node = 0, depth = 0;   // tree = game * roots + root
   int path[kSearchDepth + 2];
   int path_len = 0;
   long slot = -1;     // first queue slot of the expansion this playout requested (parent board, then the evaluated
                       // children); -1 when it only waits for an expansion another playout requested
 };
 
-struct GameState {
-  Position pos;
+// One search tree. A move is searched by `roots` independent trees from the same position (the reference's
+// root-parallel threads, tree.cpp:153-196: DEFAULT_NUM_THREADS = 4 roots of NUM_SIMULATIONS_PER_THREAD playouts each, own
+// Dirichlet noise), merged like Node::combineNodes (tree.cpp:122-142) before the move is chosen.
+struct Tree {
   std::vector<Node> arena;
   std::vector<ChildStat> stat;     // parallel to arena
   void refresh(int i) { const Node &n = arena[i]; stat[i].q = n.value(); stat[i].u = n.prior / (n.visits + 1); }
-  int launched = 0, done = 0, moves_played = 0;
+  int launched = 0, done = 0;
+};
+
+struct GameState {
+  Position pos;
+  int moves_played = 0;
   bool finished = false;
   std::vector<cases::Case> kept;   // boards of this game awaiting the game result
 };
@@ -90,6 +98,8 @@ struct Worker {
   cab_net *net;
   cab_leafq *q = nullptr;
   std::vector<GameState> games;
+  std::vector<Tree> trees;         // games.size() * roots, the roots of a game adjacent
+  int roots = 1;
   int playouts_per_move, moves_per_game, in_flight;
   bool network_priors;
   double save_ratio = 0.0;
@@ -126,7 +136,7 @@ struct Worker {
     Move mv[kMaxMoves];
     const int n = generate_moves(p.pos, p.pos.side, mv, /*queen_only=*/true);   // std::map<Move> keeps one promotion (Q8)
     if (n == 0) return false;
-    GameState &g = games[p.game];
+    Tree &g = trees[p.tree];
     const int first = (int) g.arena.size();
     g.arena.resize(g.arena.size() + n);
     g.stat.resize(g.arena.size());
@@ -164,7 +174,7 @@ struct Worker {
 
   void finish_expansion(Playout &p, const double *res) {
     if (p.slot < 0) return;                    // this playout only waited for somebody else's expansion
-    GameState &g = games[p.game];
+    Tree &g = trees[p.tree];
     Node &n = g.arena[p.node];
     const double cm = n.color;
     const int k = n.n_children, first = n.first_child;
@@ -191,7 +201,7 @@ struct Worker {
 
   // advance until the playout parks (false) or completes (true)
   bool advance(Playout &p) {
-    GameState &g = games[p.game];
+    Tree &g = trees[p.tree];
     while (p.depth < kSearchDepth) {
       if (p.pos.over) break;
       Node &n = g.arena[p.node];
@@ -241,14 +251,14 @@ struct Worker {
     return true;
   }
 
-  void new_root(GameState &g) {
+  void new_root(Tree &g, const Position &pos) {
     g.arena.clear();
     g.arena.reserve(1 << 14);
     g.arena.emplace_back();
     g.stat.clear();
     g.stat.reserve(1 << 14);
     g.stat.emplace_back();
-    g.arena[0].color = g.pos.side;
+    g.arena[0].color = pos.side;
     g.launched = g.done = 0;
   }
 
@@ -257,7 +267,9 @@ struct Worker {
       std::fprintf(stderr, "%s\n", cab_last_error());
       std::exit(1);
     }
-    for (auto &g : games) new_root(g);
+    trees.resize(games.size() * (size_t) roots);
+    for (size_t t = 0; t < trees.size(); ++t) new_root(trees[t], games[t / roots].pos);
+    const int quota = std::max(1, playouts_per_move / roots);   // playouts per root (NUM_SIMULATIONS_PER_THREAD)
     std::vector<Playout> parked, still;
     parked.reserve(in_flight);
     bool active = true;
@@ -266,13 +278,14 @@ struct Worker {
       bool launched_any = true;
       while (launched_any && (int) parked.size() < in_flight) {
         launched_any = false;
-        for (size_t gi = 0; gi < games.size() && (int) parked.size() < in_flight; ++gi) {
-          GameState &g = games[gi];
-          if (g.finished || g.launched >= playouts_per_move) continue;
+        for (size_t ti = 0; ti < trees.size() && (int) parked.size() < in_flight; ++ti) {
+          Tree &g = trees[ti];
+          const GameState &game = games[ti / roots];
+          if (game.finished || g.launched >= quota) continue;
           if (!g.arena[0].expanded && g.launched > g.done) continue;   // one playout until the root exists
           Playout p;
-          p.pos = g.pos;
-          p.game = (int) gi;
+          p.pos = game.pos;
+          p.tree = (int) ti;
           p.node = 0;
           p.path[0] = 0;
           p.path_len = 1;
@@ -293,31 +306,46 @@ struct Worker {
         st.boards += n_eval;
         st.max_flush = std::max(st.max_flush, n_eval);
         for (auto &p : parked) {
-          GameState &g = games[p.game];
+          Tree &g = trees[p.tree];
           for (int i = 0; i < p.path_len; ++i) { Node &v = g.arena[p.path[i]]; v.visits -= 1; v.vloss -= 1; g.refresh(p.path[i]); }
           finish_expansion(p, res);
         }
         still.clear();
         for (auto &p : parked) {
-          if (advance(p)) ++games[p.game].done;
+          if (advance(p)) ++trees[p.tree].done;
           else still.push_back(p);
         }
         parked.swap(still);
       }
       // games whose search is complete: play the move with the best PUCT score (tree.cpp:195) and start a new tree
       active = false;
-      for (auto &g : games) {
+      for (size_t gi = 0; gi < games.size(); ++gi) {
+        GameState &g = games[gi];
         if (g.finished) continue;
-        if (g.done >= playouts_per_move) {
-          const Node &root = g.arena[0];
+        Tree *my = &trees[gi * (size_t) roots];
+        bool all_done = true;
+        for (int r = 0; r < roots; ++r) all_done = all_done && my[r].done >= quota;
+        if (all_done) {
+          // Node::combineNodes (tree.cpp:122-142): the roots saw the same position, so their children are the same moves
+          // in the same order; priors are averaged, visit counts and value sums added, for the children and the root
+          Node root;
+          const int k = my[0].arena[0].n_children;
           int best = -1;
           double max_score = -1.0;
+          for (int r = 0; r < roots; ++r) { root.visits += my[r].arena[0].visits; root.value_sum += my[r].arena[0].value_sum; }
           const double pf = puct_parent(root);
-          for (int i = 0; i < root.n_children; ++i) {
-            const double s = puct(pf, g.stat[root.first_child + i]);
-            if (s > max_score) { max_score = s; best = root.first_child + i; }
+          for (int i = 0; i < k; ++i) {
+            Node c;
+            for (int r = 0; r < roots; ++r) {
+              const Node &rc = my[r].arena[my[r].arena[0].first_child + i];
+              c.prior += rc.prior / roots;
+              c.visits += rc.visits;
+              c.value_sum += rc.value_sum;
+            }
+            const double sc = pf * (c.prior / (c.visits + 1)) + c.value();
+            if (sc > max_score) { max_score = sc; best = i; }
           }
-          if (best >= 0) play(g.pos, g.arena[best].move);
+          if (best >= 0) play(g.pos, my[0].arena[my[0].arena[0].first_child + best].move);
           ++g.moves_played;
           ++st.moves;
           if (save_ratio > 0.0 && std::generate_canonical<double, 53>(rng) < save_ratio) {   // NetworkStorage::saveBoard
@@ -331,7 +359,9 @@ struct Worker {
             const double result = g.pos.over ? (double) g.pos.result : 0.0;   // GameResult::evaluate, game.fwd.h:82-95
             for (auto &c : g.kept) { c.target = cases::overall_result(c.target, result); finished_cases.push_back(c); }
             g.kept.clear();
-          } else new_root(g);
+          } else {
+            for (int r = 0; r < roots; ++r) new_root(my[r], g.pos);
+          }
         }
         if (!g.finished) active = true;
       }
@@ -354,6 +384,7 @@ int main(int argc, char **argv) {
   const unsigned long long seed = argc > 9 ? std::strtoull(argv[9], nullptr, 10) : 1234;
   const char *cases_path = argc > 10 && std::strcmp(argv[10], "-") != 0 ? argv[10] : nullptr;
   const int precision = argc > 12 && std::strcmp(argv[12], "f16") == 0 ? 1 : 0;
+  const int roots = argc > 13 ? std::max(1, std::atoi(argv[13])) : 1;
   const double save_ratio = cases_path ? (argc > 11 ? std::atof(argv[11]) : 0.1) : 0.0;
   cab_net *net = nullptr;
   if (cab_net_load_text(argv[1], device, &net) != CAB_OK) { std::fprintf(stderr, "%s\n", cab_last_error()); return 1; }
@@ -368,6 +399,7 @@ int main(int argc, char **argv) {
     w.network_priors = network_priors;
     w.save_ratio = save_ratio;
     w.precision = precision;
+    w.roots = roots;
     w.rng.seed(seed + 7919ull * t);
     const int lo = games * t / threads, hi = games * (t + 1) / threads;
     w.games.resize(hi - lo);
@@ -396,10 +428,10 @@ int main(int argc, char **argv) {
   std::printf("{\"config\": \"MCTS self-play, virtual-loss leaf batching\", \"games\": %d, \"playouts_per_move\": %d, \"moves_per_game\": %d, "
               "\"threads\": %d, \"in_flight_per_thread\": %d, \"network_priors\": %d, \"seconds\": %.3f, \"moves_played\": %ld, "
               "\"playouts\": %ld, \"playouts_per_s\": %.1f, \"boards_evaluated\": %ld, \"boards_per_s\": %.1f, \"expansions\": %ld, "
-              "\"flushes\": %ld, \"avg_boards_per_flush\": %.1f, \"max_boards_per_flush\": %ld, \"gpu_launches\": %ld, \"cases_written\": %ld, \"gpu_wait_fraction\": %.3f, \"precision\": \"%s\"}\n",
+              "\"flushes\": %ld, \"avg_boards_per_flush\": %.1f, \"max_boards_per_flush\": %ld, \"gpu_launches\": %ld, \"cases_written\": %ld, \"gpu_wait_fraction\": %.3f, \"precision\": \"%s\", \"roots\": %d}\n",
               games, playouts, moves, threads, in_flight, (int) network_priors, secs, tot.moves, tot.playouts, tot.playouts / secs,
               tot.boards, tot.boards / secs, tot.expansions, tot.flushes, tot.flushes ? (double) tot.boards / tot.flushes : 0.0,
-              tot.max_flush, launches, n_cases, tot.flush_seconds / (secs * threads), precision ? "f16" : "fp64");
+              tot.max_flush, launches, n_cases, tot.flush_seconds / (secs * threads), precision ? "f16" : "fp64", roots);
   cab_net_destroy(net);
   return 0;
 }

@@ -114,6 +114,10 @@ def test_selfplay_driver_on_the_fast_rules_engine(cab, golden, tmp_path):
     assert r["moves_played"] == 32 * 2 and r["playouts"] == 32 * 2 * 60
     assert r["boards_evaluated"] > r["expansions"] * 15           # parent + ~20-30 children per expansion
     assert r["avg_boards_per_flush"] > 500 and r["flushes"] < r["expansions"] / 10
+    # the reference's default search shape: 4 root-parallel trees of 125 playouts, merged like Node::combineNodes
+    out4 = subprocess.check_output([exe, latest, "16", "500", "2", "4", "64", "1", "0", "7", "-", "0", "fp64", "4"], timeout=300)
+    r4 = json.loads(out4.decode().strip().splitlines()[-1])
+    assert r4["roots"] == 4 and r4["moves_played"] == 16 * 2 and r4["playouts"] == 16 * 2 * 4 * 125
     out0 = subprocess.check_output([exe, latest, "8", "40", "1", "2", "16", "0"], timeout=300)   # shipped inverted priors
     r0 = json.loads(out0.decode().strip().splitlines()[-1])
     assert r0["playouts"] == 8 * 40 and r0["boards_evaluated"] == r0["expansions"]               # only the parent board
