@@ -10,8 +10,8 @@
 //     fetched once per CTA with TMA bulk copies
 //   * activations never touch shared or global memory: the A operand of every layer is read FROM TENSOR MEMORY
 //     (tcgen05.mma ... [d], [a], b_desc: SASS UTCHMMA with a TMEM A operand). A layer's accumulator row is loaded by its
-//     thread (tcgen05.ld), put through f(x) = 4 tanh(x/4), packed to fp16 and stored straight back (tcgen05.st) as the
-//     next layer's A row — lane t only ever touches lane t, so there is no shuffle and no layout change
+//     thread (tcgen05.ld), put through the activation (carried as tanh(x/4), see act_pack_h2), packed to fp16 and
+//     stored straight back (tcgen05.st) as the next layer's A row — lane t only ever touches lane t, so there is no shuffle and no layout change
 //   * TMEM columns: [0, 128) the A operand (up to 256 fp16 per row), [128, 384) the fp32 accumulator
 //   * the last layer (N = 1) is a dot product inside the thread that already holds the row
 #pragma once
@@ -71,6 +71,18 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// The activation on two accumulator values at once, result already packed as the fp16 pair the next layer reads.
+// f(x) = 4 tanh(x / 4), but neither factor 4 is computed here: the kernel carries t = tanh(x / 4) = a / 4 between the
+// layers. A layer fed with t instead of a = 4 t and asked for x / 4 instead of x needs its weights times 4 / 4 = 1, so
+// only the FIRST layer's image is scaled (by 1/4, exact: its input is k * 0.4, not a tanh) and the output is 4 * tanh of
+// the last dot product. The epilogue is then one cvt.rn.f16x2.f32 and ONE tanh.approx.f16x2 per pair of values.
+__device__ __forceinline__ uint32_t act_pack_h2(float a, float b) {
+  const __half2 q = __floats2half2_rn(a, b);
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t *>(&q)));
+  return t;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_fused_kernel(const FusedArgs args) {
@@ -166,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_fused_kernel(const FusedAr
           uint32_t r[16], packed[8];
           tmem_ld16(lane_base + kColD + c, r);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) packed[i] = pack_h2(tc::act_f32(__uint_as_float(r[2 * i])), tc::act_f32(__uint_as_float(r[2 * i + 1])));
+          for (int i = 0; i < 8; ++i) packed[i] = act_pack_h2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
           tmem_st8(lane_base + kColA + c / 2, packed);
         }
         tmem_wait_st();                                // (n_pad is the next layer's K: no K padding left to zero)
@@ -177,14 +189,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_fused_kernel(const FusedAr
           uint32_t r[16];
           tmem_ld16(lane_base + kColD + c, r);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dot = fmaf(tc::act_f32(__uint_as_float(r[i])), w_last[c + i], dot);
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t h = act_pack_h2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            const float2 v = __half22float2(*reinterpret_cast<const __half2 *>(&h));
+            dot = fmaf(v.x, w_last[c + 2 * i], dot);
+            dot = fmaf(v.y, w_last[c + 2 * i + 1], dot);
+          }
         }
       }
     }
     if (half == 1) dot_half[row_in_tile] = dot;
     tc::tmem_fence_before();
     __syncthreads();                                 // the accumulator has been read: the next tile may overwrite it
-    if (half == 0 && valid) args.out[board] = (double) tc::act_f32(dot + dot_half[row_in_tile]);
+    if (half == 0 && valid) {
+      float y;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(dot + dot_half[row_in_tile]));   // the sum already is x / 4
+      args.out[board] = (double) (4.0f * y);
+    }
   }
 
   tc::tmem_fence_before();
@@ -212,7 +233,8 @@ __global__ void __launch_bounds__(256) f16_pack_kernel(const PackArgs a) {
     const long total = (long) a.n_pad[l] * a.k_pad[l];
     for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < total; i += (long) gridDim.x * blockDim.x) {
       const int n = (int) (i / a.k_pad[l]), k = (int) (i % a.k_pad[l]);
-      const double v = (n < a.N[l] && k < a.K[l]) ? a.w[a.woff[l] + (long) k * a.N[l] + n] : 0.0;   // W is [K][N]
+      double v = (n < a.N[l] && k < a.K[l]) ? a.w[a.woff[l] + (long) k * a.N[l] + n] : 0.0;   // W is [K][N]
+      if (l == 0) v *= 0.25;      // the kernel carries tanh(x / 4) between layers (see act_pack_h2): only layer 0 is rescaled
       const uint32_t off = a.w_off[l] + (uint32_t) (k >> 6) * (uint32_t) a.n_pad[l] * 128u + (uint32_t) (n >> 3) * 1024u +
                            (uint32_t) (n & 7) * 128u + (uint32_t) ((((k & 63) >> 3) ^ (n & 7)) * 16) + (uint32_t) (k & 7) * 2u;
       *reinterpret_cast<__half *>(a.image + off) = __double2half(v);
