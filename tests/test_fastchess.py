@@ -98,3 +98,29 @@ def test_material_rule(fc):
     sq[59] = 0                                             # remove the black queen
     fc.fc_set(p, sq.ctypes.data_as(C.POINTER(C.c_byte)), 1, 0)
     assert fc.fc_material(p, 1) == 9.0 and fc.fc_material(p, -1) == -9.0
+
+
+def test_move_generation_is_colour_symmetric(fc):
+    """Mirroring a position (rows reversed, colours swapped, side to move swapped) must mirror its legal moves: an
+    internal consistency check of the rules engine that does not depend on the recorded games' side to move."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "chess_games.npz"))
+    codes, side, nocap = g["codes"], g["side"], g["nocap"]
+    rng = np.random.default_rng(3)
+    p, buf = new_pos(fc), (C.c_ubyte * (3 * 256))()
+
+    def moves_of(c, s, nc):
+        fc.fc_set(p, np.ascontiguousarray(c).ctypes.data_as(C.POINTER(C.c_byte)), int(s), int(nc))
+        n = fc.fc_moves(p, buf, 0)
+        return {(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]) for i in range(n)}
+
+    def flip_sq(sq):
+        return (7 - (sq >> 3)) * 8 + (sq & 7)
+
+    checked = 0
+    for i in rng.choice(len(codes), size=600, replace=False):
+        mirrored = (-codes[i].reshape(8, 8)[::-1]).reshape(64)
+        a = moves_of(codes[i], side[i], nocap[i])
+        b = moves_of(mirrored, -side[i], nocap[i])
+        assert {(flip_sq(f), flip_sq(t), pr) for f, t, pr in a} == b, int(i)
+        checked += len(a)
+    assert checked > 10000
