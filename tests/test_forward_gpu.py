@@ -4,6 +4,7 @@ against the pinned oracle and the golden vectors produced by the reference's own
 Tolerance (BASELINE.json north_star): 1e-5 RELATIVE on the reference-precision (fp64) path. The absolute floor
 1e-12 only guards outputs that are numerically zero; the smallest golden |y| is 3.4e-7.
 """
+import importlib
 import os
 
 import numpy as np
@@ -202,3 +203,24 @@ def test_prediction_matches_the_reference_decider(cab, net, golden):
     ev1, pri = net.prediction(g["codes"][0], int(g["side"][0]), network_priors=True)
     ev0, bug = net.prediction(g["codes"][0], int(g["side"][0]))
     assert ev1 == ev0 and [m for m, _ in pri] == [m for m, _ in bug] and all(abs(l) < 4.0 for _, l in pri)
+
+
+def test_full_size_batch_is_piecewise_consistent(cab, net, golden):
+    """BASELINE.json configs[1] size (2^20 boards, here + 37 for a ragged tail): every board's result is independent of
+    where in which launch it was computed — the whole equals its pieces bit for bit, in any order."""
+    synth = importlib.import_module("chess-ai_b200.synth")
+    n = (1 << 20) + 37
+    base = synth.synthetic_boards(1 << 17, seed=5)
+    rng = np.random.default_rng(9)
+    codes = np.ascontiguousarray(base[rng.integers(0, len(base), size=n)])      # 2^20 + 37 draws from 131 072 distinct boards
+    y = net.predict_batch(codes)
+    assert y.shape == (n,) and np.all(np.isfinite(y)) and np.abs(y).max() <= 4.0
+    cuts = [0, 1, 4097, 300_000, 300_008, 777_777, n]
+    pieces = np.concatenate([net.predict_batch(codes[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert np.array_equal(pieces, y)
+    ref = net.predict_batch(base)                                               # each distinct board once
+    idx = rng.integers(0, n, size=5000)
+    back = {tuple(codes[i]): y[i] for i in idx}
+    lookup = {tuple(b): v for b, v in zip(base[:20000], ref[:20000])}
+    hits = [(back[k], lookup[k]) for k in back if k in lookup]
+    assert len(hits) > 100 and all(a == b for a, b in hits)
