@@ -68,6 +68,8 @@ _SIGS = {
     "cab_leafq_set_precision": [_vp, C.c_int],
     "cab_prediction_host": [_vp, _i8p, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), _f64p, C.c_int, _ip],
     "cab_leafq_flush": [_vp, _lp],
+    "cab_leafq_flush_async": [_vp, _lp],
+    "cab_leafq_wait": [_vp],
     "cab_leafq_results": [_vp, C.POINTER(_dp)],
     "cab_leafq_stats": [_vp, _lp, _lp, _lp],
     "cab_prior_softmax_host": [C.c_int, _f64p, _i32p, C.c_int, _f64p, _f64p],

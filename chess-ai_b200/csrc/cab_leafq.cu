@@ -48,6 +48,7 @@ struct cab_leafq {
   std::atomic<long> head{0};
   long launches = 0, flushes = 0, evaluated = 0;
   bool f16 = false;            // evaluate with the reduced-precision fused tcgen05 kernel (cab_leafq_set_precision)
+  long in_flight = -1;         // boards of the flush queued by cab_leafq_flush_async and not yet waited for
 };
 
 using namespace cab;
@@ -104,11 +105,14 @@ int cab_leafq_pending(cab_leafq *q, long *n) {
   return CAB_OK;
 }
 
-// Not concurrent with push. Evaluates slots [0, pending) and empties the queue.
-int cab_leafq_flush(cab_leafq *q, long *n_evaluated) {
+// Queues the evaluation of slots [0, pending) on the queue's streams (H2D, launches, D2H) and returns without waiting.
+// No push until cab_leafq_wait. A thread that owns two queues can walk its trees for one while the GPU works on the other.
+int cab_leafq_flush_async(cab_leafq *q, long *n_evaluated) {
   if (!q) { set_error("null argument"); return CAB_EINVAL; }
+  if (q->in_flight >= 0) { set_error("a flush of this queue is already in flight: cab_leafq_wait first"); return CAB_ESTATE; }
   const long n = q->head.load();
   if (n_evaluated) *n_evaluated = n;
+  q->in_flight = n;
   if (n == 0) return CAB_OK;
   cab_net *net = q->net;
   CAB_CUDA(cudaSetDevice(net->device));
@@ -124,10 +128,6 @@ int cab_leafq_flush(cab_leafq *q, long *n_evaluated) {
       CAB_CUDA(cudaMemcpyAsync(q->h_out + b0, q->d_out + b0, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
       ++q->launches;
     }
-    for (auto s : q->streams) CAB_CUDA(cudaStreamSynchronize(s));
-    ++q->flushes;
-    q->evaluated += n;
-    q->head.store(0);
     return CAB_OK;
   }
   if (net->pack_dirty) {  // weights changed since the last evaluation (rare): re-pack once, under the net's lock
@@ -146,11 +146,30 @@ int cab_leafq_flush(cab_leafq *q, long *n_evaluated) {
     CAB_CUDA(cudaMemcpyAsync(q->h_out + b0, q->d_out + b0, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
     ++q->launches;
   }
-  for (auto s : q->streams) CAB_CUDA(cudaStreamSynchronize(s));
-  ++q->flushes;
-  q->evaluated += n;
+  return CAB_OK;
+}
+
+// Waits for the flush in flight (if any); the results are then valid and the queue is empty again.
+int cab_leafq_wait(cab_leafq *q) {
+  if (!q) { set_error("null argument"); return CAB_EINVAL; }
+  if (q->in_flight < 0) return CAB_OK;
+  const long n = q->in_flight;
+  q->in_flight = -1;
+  if (n > 0) {
+    CAB_CUDA(cudaSetDevice(q->net->device));
+    for (auto s : q->streams) CAB_CUDA(cudaStreamSynchronize(s));
+    ++q->flushes;
+    q->evaluated += n;
+  }
   q->head.store(0);
   return CAB_OK;
+}
+
+// Not concurrent with push. Evaluates slots [0, pending) and empties the queue.
+int cab_leafq_flush(cab_leafq *q, long *n_evaluated) {
+  const int rc = cab_leafq_flush_async(q, n_evaluated);
+  if (rc != CAB_OK) { if (q) q->in_flight = -1; return rc; }
+  return cab_leafq_wait(q);
 }
 
 // precision = 0: the fp64 reference-precision kernel (default); 1: the fused fp16 tcgen05 kernel (cab_eval_f16_*: nets

@@ -106,6 +106,10 @@ CAB_API int cab_leafq_pending(cab_leafq *q, long *n_boards);
 /* 0 = fp64 reference precision (default), 1 = the fused fp16 tcgen05 kernel (reduced precision, cab_eval_f16_*) */
 CAB_API int cab_leafq_set_precision(cab_leafq *q, int precision);
 CAB_API int cab_leafq_flush(cab_leafq *q, long *n_evaluated);
+/* The same in two halves: flush_async queues H2D + launches + D2H and returns; wait blocks until the results are valid and
+ * empties the queue. No push in between. A search thread with two queues overlaps its tree walk with the GPU. */
+CAB_API int cab_leafq_flush_async(cab_leafq *q, long *n_evaluated);
+CAB_API int cab_leafq_wait(cab_leafq *q);
 CAB_API int cab_leafq_results(cab_leafq *q, const double **results_by_slot);
 CAB_API int cab_leafq_stats(cab_leafq *q, long *launches, long *flushes, long *evaluated);
 /* K7 — priors of expanded nodes (MCTS::expand_node, tree.cpp:299-306 + Node::expand :92): node s owns

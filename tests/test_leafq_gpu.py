@@ -146,3 +146,27 @@ def test_leaf_queue_reduced_precision_option(cab, golden):
     with pytest.raises(cab.CabError):
         cab._ck(L.cab_leafq_set_precision(q, 7))
     cab._ck(L.cab_leafq_destroy(q))
+
+
+def test_leaf_queue_async_flush_and_wait(cab, golden):
+    """cab_leafq_flush_async + cab_leafq_wait = cab_leafq_flush; a second async flush before the wait is refused."""
+    import ctypes as C
+    L = cab.lib()
+    net = cab.Network.from_weights([64, 144, 225, 100, 1], golden["latest_weights"])
+    codes = np.ascontiguousarray(golden["syn_codes"][:5000])
+    q = C.c_void_p()
+    cab._ck(L.cab_leafq_create(net._h, 8192, 4096, 2, C.byref(q)))
+    slot, n_eval, res = C.c_long(-1), C.c_long(0), C.POINTER(C.c_double)()
+    cab._ck(L.cab_leafq_push(q, codes.reshape(-1), len(codes), C.byref(slot)))
+    cab._ck(L.cab_leafq_flush_async(q, C.byref(n_eval)))
+    assert n_eval.value == len(codes)
+    assert L.cab_leafq_flush_async(q, C.byref(n_eval)) == cab.CAB_ESTATE
+    cab._ck(L.cab_leafq_wait(q))
+    cab._ck(L.cab_leafq_results(q, C.byref(res)))
+    got = np.ctypeslib.as_array(res, shape=(len(codes),)).copy()
+    assert np.array_equal(got, net.predict_batch(codes))
+    pending = C.c_long(-1)
+    cab._ck(L.cab_leafq_pending(q, C.byref(pending)))
+    assert pending.value == 0
+    cab._ck(L.cab_leafq_wait(q))                      # nothing in flight: a no-op
+    cab._ck(L.cab_leafq_destroy(q))
