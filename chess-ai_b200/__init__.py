@@ -77,6 +77,7 @@ _SIGS = {
     "cab_eval_bf16_host": [_vp, _i8p, C.c_long, _f64p],
     "cab_eval_records_host": [_vp, _u8p, C.c_long, _f64p],
     "cab_forward_full_host": [_vp, _i8p, C.c_long, _f64p],
+    "cab_forward_thetas_host": [_vp, _i8p, C.c_long, _f64p, _f64p],
     "cab_train_case": [_vp, _i8p, C.c_double, _dp, C.c_double, C.c_double, _ip, _dp, _dp],
     "cab_train_sequence": [_vp, _i8p, _f64p, C.c_long, _dp, C.c_uint64, _vp, _ip],
     "cab_train_batch_host": [_vp, _i8p, _f64p, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp],
@@ -373,6 +374,14 @@ class Network:
         out = np.zeros((len(c), sum(self.dims[1:])), dtype=np.float64)
         _ck(lib().cab_forward_full_host(self._h, c.reshape(-1), len(c), out.reshape(-1)))
         return out
+
+    def forward_thetas(self, codes):
+        """propagate_for_training(unbounded) (network.cpp:139-153): (activations, pre-activations theta), each [B, sum(dims[1:])]."""
+        c = _as_codes(codes)
+        acts = np.zeros((len(c), sum(self.dims[1:])), dtype=np.float64)
+        thetas = np.zeros_like(acts)
+        _ck(lib().cab_forward_thetas_host(self._h, c.reshape(-1), len(c), acts.reshape(-1), thetas.reshape(-1)))
+        return acts, thetas
 
 
 # ---- network::Optimizer ---------------------------------------------------------------------------------------------

@@ -232,7 +232,6 @@ constexpr bool kDefaultJit = false;  // activation applied just-in-time on the A
 
 // CTA geometry: warp PAIRS per CTA (8 boards each), weight-ring depth, CTAs per SM. Wide layers trade pairs for
 // activation space. n_cons counts pairs. CAB_FWD_PAIRS / CAB_FWD_STAGES override for experiments.
-struct Geometry { int n_cons, n_stages, ctas_per_sm; };
 Geometry choose_geometry(int a_units, int stage_bytes, long n_boards, int sm_count) {
   static const int env_w = getenv("CAB_FWD_PAIRS") ? atoi(getenv("CAB_FWD_PAIRS")) : 0;
   static const int env_s = getenv("CAB_FWD_STAGES") ? atoi(getenv("CAB_FWD_STAGES")) : 0;
@@ -256,8 +255,10 @@ Geometry choose_geometry(int a_units, int stage_bytes, long n_boards, int sm_cou
 }
 int consumer_warps_for(int a_units, int stage_bytes) { return choose_geometry(a_units, stage_bytes, 0, 148).n_cons; }
 
-// (re)build the packed streams from d_w on `stream`
-int ensure_packed(cab_net *net, cudaStream_t stream) {
+// (re)build the packed streams from d_w on `stream`. Call with net->mu held. drain = true waits for the pack kernels
+// before the flag falls, so evaluations on OTHER streams may follow; drain = false is for callers whose next launches
+// are ordered after `stream` anyway (the trainer: same stream, or forked from it by event).
+int ensure_packed(cab_net *net, cudaStream_t stream, bool drain) {
   if (!net->pack_dirty) return CAB_OK;
   for (StreamPlan *p : {&net->fwd, &net->bwd}) {
     if (p->total_doubles == 0) continue;
@@ -266,12 +267,13 @@ int ensure_packed(cab_net *net, cudaStream_t stream) {
     net->launches++;
   }
   CAB_CUDA(cudaGetLastError());
+  if (drain) CAB_CUDA(cudaStreamSynchronize(stream));
   net->pack_dirty = false;
   return CAB_OK;
 }
 
 int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d_out, double *d_save, long save_stride,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, double *d_theta) {
   if (n_boards <= 0) return CAB_OK;
   if (!net->fp64_ok) {
     set_error("layer too wide for the fp64 stream kernel (%d activation units per pair exceed shared memory); "
@@ -293,6 +295,7 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
   a.codes = d_codes;
   a.out = d_out;
   a.save = d_save;
+  a.save_theta = d_theta;
   a.save_stride = save_stride;
   const size_t smem = forward_smem_bytes(a.a_units, n_cons, geo.n_stages, net->stage_bytes);
   const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * geo.ctas_per_sm);
@@ -321,7 +324,8 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
     net->launches++;
     return CAB_OK;
   }
-  if (jit) mlp_forward_kernel<false, true><<<grid, n_cons * 64, smem, stream>>>(a);
+  if (d_theta != nullptr) mlp_forward_kernel<false, false, true><<<grid, n_cons * 64, smem, stream>>>(a);
+  else if (jit) mlp_forward_kernel<false, true><<<grid, n_cons * 64, smem, stream>>>(a);
   else mlp_forward_kernel<false, false><<<grid, n_cons * 64, smem, stream>>>(a);
   net->launches++;
   CAB_CUDA(cudaGetLastError());
@@ -359,15 +363,8 @@ static std::vector<int> normalize_dims(const int *dims, int n) {  // network.cpp
   return d;
 }
 
-static int create_exact(const std::vector<int> &dims, int device, cab_net **out) {
-  for (int v : dims)
-    if (v <= 0 || v > 8192) { set_error("layer width %d out of range [1, 8192]", v); return CAB_EINVAL; }
-  if (dims.size() < 2 || dims.size() > 32) { set_error("bad layer count %zu", dims.size()); return CAB_EINVAL; }
-  if (dims[0] != 64) { set_error("input layer must be 64 wide (one feature per square), got %d", dims[0]); return CAB_EINVAL; }
-  int rc = select_device(device);
-  if (rc != CAB_OK) return rc;
-  cab_net *net = new cab_net();
-  net->device = device;
+static int init_net(cab_net *net, const std::vector<int> &dims, int device) {
+  int rc = CAB_OK;
   cudaDeviceProp prop;
   CAB_CUDA(cudaGetDeviceProperties(&prop, device));
   net->sm_count = prop.multiProcessorCount;
@@ -393,7 +390,22 @@ static int create_exact(const std::vector<int> &dims, int device, cab_net **out)
   net->fp64_ok = consumer_warps_for(std::max(net->fwd.a_units, net->bwd.a_units), net->stage_bytes) > 0;
   CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
+  return CAB_OK;
+}
+
+static int create_exact(const std::vector<int> &dims, int device, cab_net **out) {
+  for (int v : dims)
+    if (v <= 0 || v > 8192) { set_error("layer width %d out of range [1, 8192]", v); return CAB_EINVAL; }
+  if (dims.size() < 2 || dims.size() > 32) { set_error("bad layer count %zu", dims.size()); return CAB_EINVAL; }
+  if (dims[0] != 64) { set_error("input layer must be 64 wide (one feature per square), got %d", dims[0]); return CAB_EINVAL; }
+  int rc = select_device(device);
+  if (rc != CAB_OK) return rc;
+  cab_net *net = new cab_net();
+  net->device = device;
+  rc = init_net(net, dims, device);
+  if (rc != CAB_OK) { cab_net_destroy(net); return rc; }   // a partially built net is released, not leaked
   *out = net;
   return CAB_OK;
 }
@@ -442,8 +454,7 @@ static int eval_host_impl(cab_net *net, const int8_t *codes, const uint8_t *reco
   if (rc == CAB_OK) {
     {
       std::lock_guard<std::mutex> lk(net->mu);
-      rc = ensure_packed(net, c->stream[0]);
-      if (rc == CAB_OK && cudaStreamSynchronize(c->stream[0]) != cudaSuccess) rc = CAB_ECUDA;
+      rc = ensure_packed(net, c->stream[0], true);
     }
     int i = 0;
     for (long b0 = 0; b0 < n && rc == CAB_OK; b0 += chunk, i = (i + 1) % kCtxStreams) {
@@ -675,11 +686,7 @@ int cab_eval_dev(cab_net *net, const int8_t *codes_dev, long n, double *out_dev,
   if (rc != CAB_OK) return rc;
   {
     std::lock_guard<std::mutex> lk(net->mu);
-    if (net->pack_dirty) {
-      rc = ensure_packed(net, (cudaStream_t) stream);
-      if (rc != CAB_OK) return rc;
-      CAB_CUDA(cudaStreamSynchronize((cudaStream_t) stream));  // other streams may evaluate next
-    }
+    if ((rc = ensure_packed(net, (cudaStream_t) stream, true)) != CAB_OK) return rc;  // other streams may evaluate next
   }
   return launch_forward(net, codes_dev, n, out_dev, nullptr, 0, (cudaStream_t) stream);
 }
@@ -694,11 +701,7 @@ int cab_eval_dev_batches(cab_net *net, const int8_t *codes_dev, long n, long bat
   if (rc != CAB_OK) return rc;
   {
     std::lock_guard<std::mutex> lk(net->mu);
-    if (net->pack_dirty) {
-      rc = ensure_packed(net, (cudaStream_t) streams[0]);
-      if (rc != CAB_OK) return rc;
-      CAB_CUDA(cudaStreamSynchronize((cudaStream_t) streams[0]));
-    }
+    if ((rc = ensure_packed(net, (cudaStream_t) streams[0], true)) != CAB_OK) return rc;
   }
   int i = 0;
   for (long b0 = 0; b0 < n; b0 += batch, ++i) {
@@ -721,39 +724,61 @@ int cab_eval_records_host(cab_net *net, const uint8_t *records, long n, double *
   return eval_host_impl(net, nullptr, records, n, out);
 }
 
-int cab_forward_full_host(cab_net *net, const int8_t *codes, long n, double *acts_host) {
-  if (!net || n < 0 || (n > 0 && (!codes || !acts_host))) { set_error("bad argument"); return CAB_EINVAL; }
-  if (n == 0) return CAB_OK;
+static int forward_full_impl(cab_net *net, const int8_t *codes, long n, double *acts_host, double *thetas_host) {
   int rc = select_device(net->device);
   if (rc != CAB_OK) return rc;
   const long pad = (n + 63) / 64 * 64;
   const long stride = pad * 8;
-  int8_t *d_codes = nullptr;
-  double *d_save = nullptr, *d_out = nullptr;
-  CAB_CUDA(cudaMalloc(&d_codes, n * 64));
-  CAB_CUDA(cudaMalloc(&d_out, n * sizeof(double)));
-  CAB_CUDA(cudaMalloc(&d_save, (size_t) net->act_units_total * stride * sizeof(double)));
-  CAB_CUDA(cudaMemset(d_save, 0, (size_t) net->act_units_total * stride * sizeof(double)));
-  CAB_CUDA(cudaMemcpy(d_codes, codes, n * 64, cudaMemcpyHostToDevice));
+  const size_t tensor = (size_t) net->act_units_total * stride;
+  struct Dev {   // released on every return path
+    void *p = nullptr;
+    ~Dev() { cudaFree(p); }
+  } codes_b, out_b, save_b, theta_b;
+  CAB_CUDA(cudaMalloc(&codes_b.p, n * 64));
+  CAB_CUDA(cudaMalloc(&out_b.p, n * sizeof(double)));
+  CAB_CUDA(cudaMalloc(&save_b.p, tensor * sizeof(double)));
+  CAB_CUDA(cudaMemset(save_b.p, 0, tensor * sizeof(double)));
+  if (thetas_host != nullptr) {
+    CAB_CUDA(cudaMalloc(&theta_b.p, tensor * sizeof(double)));
+    CAB_CUDA(cudaMemset(theta_b.p, 0, tensor * sizeof(double)));
+  }
+  CAB_CUDA(cudaMemcpy(codes_b.p, codes, n * 64, cudaMemcpyHostToDevice));
   {
     std::lock_guard<std::mutex> lk(net->mu);
-    rc = ensure_packed(net, nullptr);
+    rc = ensure_packed(net, nullptr, true);
   }
-  if (rc == CAB_OK) rc = launch_forward(net, d_codes, n, d_out, d_save, stride, nullptr);
-  std::vector<double> h((size_t) net->act_units_total * stride);
-  if (rc == CAB_OK && cudaMemcpy(h.data(), d_save, h.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = CAB_ECUDA;
-  cudaFree(d_codes); cudaFree(d_out); cudaFree(d_save);
   if (rc != CAB_OK) return rc;
-  // unit layout [unit][board][8] -> board-major rows of sum(dims[1..]) doubles
+  rc = launch_forward(net, (const int8_t *) codes_b.p, n, (double *) out_b.p, (double *) save_b.p, stride, nullptr, (double *) theta_b.p);
+  if (rc != CAB_OK) return rc;
   long row = 0;
   for (size_t l = 1; l < net->dims.size(); ++l) row += net->dims[l];
-  for (long b = 0; b < n; ++b) {
-    long o = 0;
-    for (size_t l = 1; l < net->dims.size(); ++l)
-      for (int j = 0; j < net->dims[l]; ++j, ++o)
-        acts_host[b * row + o] = h[(size_t) (net->act_unit_off[l] + j / 8) * stride + b * 8 + (j % 8)];
-  }
+  std::vector<double> h(tensor);
+  // unit layout [unit][board][8] -> board-major rows of sum(dims[1..]) doubles
+  auto gather = [&](const void *dev, double *host) -> int {
+    CAB_CUDA(cudaMemcpy(h.data(), dev, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (long b = 0; b < n; ++b) {
+      long o = 0;
+      for (size_t l = 1; l < net->dims.size(); ++l)
+        for (int j = 0; j < net->dims[l]; ++j, ++o)
+          host[b * row + o] = h[(size_t) (net->act_unit_off[l] + j / 8) * stride + b * 8 + (j % 8)];
+    }
+    return CAB_OK;
+  };
+  if (acts_host != nullptr && (rc = gather(save_b.p, acts_host)) != CAB_OK) return rc;
+  if (thetas_host != nullptr && (rc = gather(theta_b.p, thetas_host)) != CAB_OK) return rc;
   return CAB_OK;
+}
+
+int cab_forward_full_host(cab_net *net, const int8_t *codes, long n, double *acts_host) {
+  if (!net || n < 0 || (n > 0 && (!codes || !acts_host))) { set_error("bad argument"); return CAB_EINVAL; }
+  if (n == 0) return CAB_OK;
+  return forward_full_impl(net, codes, n, acts_host, nullptr);
+}
+
+int cab_forward_thetas_host(cab_net *net, const int8_t *codes, long n, double *acts_host, double *thetas_host) {
+  if (!net || n < 0 || (n > 0 && (!codes || !thetas_host))) { set_error("bad argument"); return CAB_EINVAL; }
+  if (n == 0) return CAB_OK;
+  return forward_full_impl(net, codes, n, acts_host, thetas_host);
 }
 
 // ---- measurement helpers ----------------------------------------------------------------------------------------

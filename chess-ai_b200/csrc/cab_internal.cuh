@@ -89,12 +89,16 @@ struct cab_net {
   std::vector<long> woff;
   long n_weights = 0;
   double *d_w = nullptr;     // flat weights
-  bool pack_dirty = true;    // packed streams stale w.r.t. d_w
+  // stale-copy flags: set by whoever changes d_w, tested and cleared only under `mu` (evaluation) / `tc_mu` (bf16) and
+  // only after the stream that rebuilt the copy has drained, so a launch on another stream never overtakes the rebuild
+  std::atomic<bool> pack_dirty{true};    // packed streams stale w.r.t. d_w
   bool fp64_ok = true;       // the fp64 stream kernels fit this network's widest layer in shared memory
-  bool tc_dirty = true;      // bf16 copies of the tcgen05 path stale w.r.t. d_w
-  bool f16_dirty = true;     // fp16 shared-memory image of the fused tcgen05 path stale w.r.t. d_w
-  void *f16 = nullptr;       // F16State of cab_tc.cu
+  std::atomic<bool> tc_dirty{true};      // bf16 copies of the tcgen05 path stale w.r.t. d_w
+  std::atomic<bool> f16_dirty{true};     // fp16 shared-memory image of the fused tcgen05 path stale w.r.t. d_w
+  std::atomic<void *> f16{nullptr};      // F16State of cab_tc.cu, published only when fully constructed
   void *tc = nullptr;        // cab::TcState of the bf16 tcgen05 path (cab_tc.cu), created on first use
+  std::mutex tc_mu;          // the bf16 path keeps per-net scratch (activations, staging): its calls take turns
+  cudaEvent_t tc_done = nullptr;  // end of the previous bf16 call: the next one, on whatever stream, waits for it
   cab::StreamPlan fwd, bwd;
   // saved-activation geometry (units per board-group, per layer)
   std::vector<uint32_t> act_unit_off;  // per layer l (0..L-1): first unit of layer l's activations
@@ -128,6 +132,14 @@ namespace cab {
 
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+// cab_api.cu, used by the other translation units
+int ensure_packed(cab_net *net, cudaStream_t stream, bool drain);
+int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d_out, double *d_save, long save_stride,
+                   cudaStream_t stream, double *d_theta = nullptr);
+struct Geometry { int n_cons, n_stages, ctas_per_sm; };
+Geometry choose_geometry(int a_units, int stage_bytes, long n_boards, int sm_count);
+size_t forward_smem_bytes(int a_units, int n_cons, int n_stages, int stage_bytes);
 
 #define CAB_CUDA(call)                                                         \
   do {                                                                         \

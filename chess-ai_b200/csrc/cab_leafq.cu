@@ -12,11 +12,6 @@
 
 #include "cab_internal.cuh"
 
-namespace cab {
-int ensure_packed(cab_net *net, cudaStream_t stream);
-int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d_out, double *d_save, long save_stride,
-                   cudaStream_t stream);
-}  // namespace cab
 extern "C" int cab_eval_f16_dev(cab_net *net, const int8_t *codes_dev, long n, double *out_dev, void *stream);
 namespace cab {
 
@@ -53,23 +48,32 @@ struct cab_leafq {
 
 using namespace cab;
 
-extern "C" {
-
-int cab_leafq_create(cab_net *net, long capacity, long batch, int n_streams, cab_leafq **out) {
-  if (!net || !out || capacity <= 0 || batch <= 0 || n_streams <= 0 || n_streams > 32) { set_error("bad argument"); return CAB_EINVAL; }
-  CAB_CUDA(cudaSetDevice(net->device));
-  cab_leafq *q = new cab_leafq();
-  q->net = net; q->capacity = capacity; q->batch = batch; q->n_streams = n_streams;
-  CAB_CUDA(cudaMallocHost(&q->h_codes, capacity * 64));
-  CAB_CUDA(cudaMallocHost(&q->h_out, capacity * sizeof(double)));
-  CAB_CUDA(cudaMalloc(&q->d_codes, capacity * 64));
-  CAB_CUDA(cudaMalloc(&q->d_out, capacity * sizeof(double)));
-  q->streams.resize(n_streams);
-  q->events.resize(n_streams);
-  for (int i = 0; i < n_streams; ++i) {
+static int leafq_allocate(cab_leafq *q) {
+  CAB_CUDA(cudaMallocHost(&q->h_codes, q->capacity * 64));
+  CAB_CUDA(cudaMallocHost(&q->h_out, q->capacity * sizeof(double)));
+  CAB_CUDA(cudaMalloc(&q->d_codes, q->capacity * 64));
+  CAB_CUDA(cudaMalloc(&q->d_out, q->capacity * sizeof(double)));
+  q->streams.assign(q->n_streams, nullptr);
+  q->events.assign(q->n_streams, nullptr);
+  for (int i = 0; i < q->n_streams; ++i) {
     CAB_CUDA(cudaStreamCreateWithFlags(&q->streams[i], cudaStreamNonBlocking));
     CAB_CUDA(cudaEventCreateWithFlags(&q->events[i], cudaEventDisableTiming));
   }
+  return CAB_OK;
+}
+
+extern "C" {
+
+int cab_leafq_destroy(cab_leafq *q);
+
+int cab_leafq_create(cab_net *net, long capacity, long batch, int n_streams, cab_leafq **out) {
+  if (!net || !out || capacity <= 0 || batch <= 0 || n_streams <= 0 || n_streams > 32) { set_error("bad argument"); return CAB_EINVAL; }
+  *out = nullptr;
+  CAB_CUDA(cudaSetDevice(net->device));
+  cab_leafq *q = new cab_leafq();
+  q->net = net; q->capacity = capacity; q->batch = batch; q->n_streams = n_streams;
+  const int rc = leafq_allocate(q);
+  if (rc != CAB_OK) { cab_leafq_destroy(q); return rc; }   // a partially built queue is released, not leaked
   *out = q;
   return CAB_OK;
 }
@@ -77,23 +81,26 @@ int cab_leafq_create(cab_net *net, long capacity, long batch, int n_streams, cab
 int cab_leafq_destroy(cab_leafq *q) {
   if (!q) return CAB_OK;
   cudaSetDevice(q->net->device);
-  for (auto s : q->streams) cudaStreamDestroy(s);
-  for (auto e : q->events) cudaEventDestroy(e);
+  for (auto s : q->streams) if (s) cudaStreamDestroy(s);
+  for (auto e : q->events) if (e) cudaEventDestroy(e);
   cudaFreeHost(q->h_codes); cudaFreeHost(q->h_out); cudaFree(q->d_codes); cudaFree(q->d_out);
   delete q;
   return CAB_OK;
 }
 
-// Thread-safe. Reserves n consecutive slots and copies the boards in; *first_slot is the ticket for the results.
-// CAB_ESTATE when the queue is full (flush first).
+// Thread-safe among pushers. Reserves n consecutive slots (compare-and-swap: a reservation either fits entirely or
+// leaves `head` untouched, so no pusher ever sees an inflated head or shares a slot) and copies the boards in;
+// *first_slot is the ticket for the results. CAB_ESTATE when the queue is full (flush first).
+// The copy happens AFTER the reservation: a flush must not overlap pushes that are still in progress.
 int cab_leafq_push(cab_leafq *q, const int8_t *codes, long n, long *first_slot) {
   if (!q || !codes || n <= 0 || !first_slot) { set_error("bad argument"); return CAB_EINVAL; }
-  const long at = q->head.fetch_add(n);
-  if (at + n > q->capacity) {
-    q->head.fetch_sub(n);
-    set_error("leaf queue full (%ld + %ld > %ld): flush it", at, n, q->capacity);
-    return CAB_ESTATE;
-  }
+  long at = q->head.load(std::memory_order_relaxed);
+  do {
+    if (at + n > q->capacity) {
+      set_error("leaf queue full (%ld + %ld > %ld): flush it", at, n, q->capacity);
+      return CAB_ESTATE;
+    }
+  } while (!q->head.compare_exchange_weak(at, at + n, std::memory_order_acq_rel, std::memory_order_relaxed));
   memcpy(q->h_codes + at * 64, codes, (size_t) n * 64);
   *first_slot = at;
   return CAB_OK;
@@ -130,11 +137,11 @@ int cab_leafq_flush_async(cab_leafq *q, long *n_evaluated) {
     }
     return CAB_OK;
   }
-  if (net->pack_dirty) {  // weights changed since the last evaluation (rare): re-pack once, under the net's lock
+  {  // weights changed since the last evaluation (rare): re-pack once. The flag is only ever read under the net's lock
+     // and cleared after the pack stream has drained, so no other thread's launch can overtake the pack kernels.
     std::lock_guard<std::mutex> lk(net->mu);
-    int rc = ensure_packed(net, q->streams[0]);
+    const int rc = ensure_packed(net, q->streams[0], true);
     if (rc != CAB_OK) return rc;
-    CAB_CUDA(cudaStreamSynchronize(q->streams[0]));
   }
   int i = 0;
   for (long b0 = 0; b0 < n; b0 += q->batch, ++i) {

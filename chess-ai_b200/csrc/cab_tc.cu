@@ -84,13 +84,43 @@ static bool f16_supported(const cab_net *net) {
   return true;
 }
 
-static void f16_free(cab_net *net) {
-  F16State *s = static_cast<F16State *>(net->f16);
+static void f16_delete(F16State *s) {
   if (!s) return;
   cudaFree(s->image); cudaFree(s->d_codes); cudaFree(s->d_out);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
+}
+static void f16_free(cab_net *net) {
+  f16_delete(static_cast<F16State *>(net->f16.load()));
   net->f16 = nullptr;
+}
+
+// geometry of the image + device allocations of a new state
+static int f16_construct(cab_net *net, F16State *s) {
+  uint32_t off = 0;
+  for (int l = 0; l < 3; ++l) {
+    const int K = net->dims[l], N = net->dims[l + 1];
+    const int kp = l == 0 ? 64 : (s->pack.n_pad[l - 1] + 63) / 64 * 64;   // next K = previous padded width, in 64-blocks
+    const int np = (N + 15) / 16 * 16;
+    s->pack.K[l] = K; s->pack.N[l] = N; s->pack.woff[l] = net->woff[l];
+    s->pack.k_pad[l] = kp; s->pack.n_pad[l] = np; s->pack.w_off[l] = off;
+    s->args.k_pad[l] = kp; s->args.n_pad[l] = np; s->args.w_off[l] = off;
+    s->args.k_steps[l] = l == 0 ? 4 : s->pack.n_pad[l - 1] / 16;   // the A row holds exactly the previous padded width
+    off += (uint32_t) np * (uint32_t) kp * 2u;     // np multiple of 8 and kp of 64: every K block is a whole number of 1 KB atoms
+  }
+  s->pack.K[3] = net->dims[3]; s->pack.N[3] = 1; s->pack.woff[3] = net->woff[3];
+  s->pack.w_last_off = s->args.w_last_off = off;
+  off += (uint32_t) s->pack.n_pad[2] * 4u;
+  off = (off + 15u) & ~15u;
+  s->args.image_bytes = off;
+  s->smem = (size_t) off + 1024 + 64 + tcf::kTile * sizeof(float);   // image, alignment slack, barriers, partial dot products
+  if (s->smem > 227 * 1024) { set_error("the fp16 weight image (%u bytes) does not fit shared memory", off); return CAB_EINVAL; }
+  CAB_CUDA(cudaMalloc(&s->image, off));
+  s->pack.image = s->image;
+  s->args.image = s->image;
+  CAB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CAB_CUDA(cudaFuncSetAttribute(tcf::mlp_tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem));
+  return CAB_OK;
 }
 
 // Builds the state / the weight image on first use and after a weight change, under the net's lock (double-checked: the
@@ -100,50 +130,35 @@ static int f16_prepare(cab_net *net, cudaStream_t stream) {
     set_error("the fused fp16 path needs a net shaped {64, N1, N2, N3, 1} with N1, N2, N3 <= 256");
     return CAB_EINVAL;
   }
-  if (net->f16 != nullptr && !net->f16_dirty) return CAB_OK;
+  if (net->f16.load(std::memory_order_acquire) != nullptr && !net->f16_dirty) return CAB_OK;
   std::lock_guard<std::mutex> lk(net->mu);
-  F16State *s = static_cast<F16State *>(net->f16);
-  if (!s) {
+  F16State *s = static_cast<F16State *>(net->f16.load());
+  bool fresh = false;
+  if (!s) {   // built aside and published only when complete: a failed construction leaves the net without a state
     s = new F16State();
-    net->f16 = s;
-    uint32_t off = 0;
-    for (int l = 0; l < 3; ++l) {
-      const int K = net->dims[l], N = net->dims[l + 1];
-      const int kp = l == 0 ? 64 : (s->pack.n_pad[l - 1] + 63) / 64 * 64;   // next K = previous padded width, in 64-blocks
-      const int np = (N + 15) / 16 * 16;
-      s->pack.K[l] = K; s->pack.N[l] = N; s->pack.woff[l] = net->woff[l];
-      s->pack.k_pad[l] = kp; s->pack.n_pad[l] = np; s->pack.w_off[l] = off;
-      s->args.k_pad[l] = kp; s->args.n_pad[l] = np; s->args.w_off[l] = off;
-      s->args.k_steps[l] = l == 0 ? 4 : s->pack.n_pad[l - 1] / 16;   // the A row holds exactly the previous padded width
-      off += (uint32_t) np * (uint32_t) kp * 2u;     // np multiple of 8 and kp of 64: every K block is a whole number of 1 KB atoms
-    }
-    s->pack.K[3] = net->dims[3]; s->pack.N[3] = 1; s->pack.woff[3] = net->woff[3];
-    s->pack.w_last_off = s->args.w_last_off = off;
-    off += (uint32_t) s->pack.n_pad[2] * 4u;
-    off = (off + 15u) & ~15u;
-    s->args.image_bytes = off;
-    s->smem = (size_t) off + 1024 + 64 + tcf::kTile * sizeof(float);   // image, alignment slack, barriers, partial dot products
-    if (s->smem > 227 * 1024) { set_error("the fp16 weight image (%u bytes) does not fit shared memory", off); return CAB_EINVAL; }
-    CAB_CUDA(cudaMalloc(&s->image, off));
-    s->pack.image = s->image;
-    s->args.image = s->image;
-    CAB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CAB_CUDA(cudaFuncSetAttribute(tcf::mlp_tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem));
+    const int rc = f16_construct(net, s);
+    if (rc != CAB_OK) { f16_delete(s); return rc; }
+    fresh = true;
   }
   if (net->f16_dirty) {
     s->pack.w = net->d_w;
     tcf::f16_pack_kernel<<<64, 256, 0, stream ? stream : s->stream>>>(s->pack);
     net->launches++;
-    CAB_CUDA(cudaGetLastError());
-    CAB_CUDA(cudaStreamSynchronize(stream ? stream : s->stream));   // rare (weights changed); later launches may use other streams
+    const cudaError_t e1 = cudaGetLastError();
+    const cudaError_t e2 = cudaStreamSynchronize(stream ? stream : s->stream);   // rare (weights changed); later launches may use other streams
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      if (fresh) f16_delete(s);
+      return cuda_fail(e1 != cudaSuccess ? e1 : e2, "f16_pack_kernel", __FILE__, __LINE__);
+    }
     net->f16_dirty = false;
   }
+  if (fresh) net->f16.store(s, std::memory_order_release);
   return CAB_OK;
 }
 
 // the launch itself; the caller has run f16_prepare
 static int f16_launch(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream) {
-  F16State *s = static_cast<F16State *>(net->f16);
+  F16State *s = static_cast<F16State *>(net->f16.load(std::memory_order_acquire));
   tcf::FusedArgs a = s->args;
   a.codes = d_codes;
   a.n_boards = n;
@@ -161,6 +176,7 @@ static int f16_forward(cab_net *net, const int8_t *d_codes, long n, double *d_ou
 
 void tc_free(cab_net *net) {
   f16_free(net);
+  if (net->tc_done) { cudaEventDestroy(net->tc_done); net->tc_done = nullptr; }
   TcState *s = static_cast<TcState *>(net->tc);
   if (!s) return;
   for (auto *p : s->wt) cudaFree(p);
@@ -185,7 +201,8 @@ static int tc_prepare(cab_net *net, long n, cudaStream_t stream) {
   const int L = (int) net->dims.size();
   if (!s) {
     s = new TcState();
-    net->tc = s;
+    net->tc = s;   // (under tc_mu; a failure below leaves a state tc_free releases and the next call completes: every
+                   //  allocation further down is guarded by its own null / capacity test)
     for (int l = 0; l + 2 < L; ++l) {
       __nv_bfloat16 *p = nullptr;
       CAB_CUDA(cudaMalloc(&p, (size_t) net->dims[l] * net->dims[l + 1] * 2));
@@ -394,6 +411,19 @@ int tc_grad(cab_net *net, const int8_t *d_codes, const double *d_targets, long n
   return CAB_OK;
 }
 
+// The bf16 path works in per-net scratch (packed weights, ping-pong activations, staging), so its calls take turns:
+// the caller holds net->tc_mu from tc_turn_begin to tc_turn_end, and the device work of a call is ordered after the
+// previous call's on whatever stream that one ran (event), so concurrent host threads / streams stay correct.
+int tc_turn_begin(cab_net *net, cudaStream_t stream) {
+  if (net->tc_done == nullptr) { CAB_CUDA(cudaEventCreateWithFlags(&net->tc_done, cudaEventDisableTiming)); return CAB_OK; }
+  CAB_CUDA(cudaStreamWaitEvent(stream, net->tc_done, 0));
+  return CAB_OK;
+}
+int tc_turn_end(cab_net *net, cudaStream_t stream) {
+  CAB_CUDA(cudaEventRecord(net->tc_done, stream));
+  return CAB_OK;
+}
+
 int tc_forward_out(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream) {
   return tc_forward(net, d_codes, n, d_out, stream);
 }
@@ -410,7 +440,13 @@ int cab_eval_bf16_dev(cab_net *net, const int8_t *codes_dev, long n, double *out
   if (!net || n < 0 || (n > 0 && (!codes_dev || !out_dev))) { set_error("bad argument"); return CAB_EINVAL; }
   if (n == 0) return CAB_OK;
   CAB_CUDA(cudaSetDevice(net->device));
-  return tc_forward(net, codes_dev, n, out_dev, (cudaStream_t) stream);
+  std::lock_guard<std::mutex> turn(net->tc_mu);
+  int rc = tc_prepare(net, n, (cudaStream_t) stream);   // creates the state's own stream, used when `stream` is null
+  if (rc != CAB_OK) return rc;
+  cudaStream_t s = stream ? (cudaStream_t) stream : static_cast<TcState *>(net->tc)->stream;
+  if ((rc = tc_turn_begin(net, s)) != CAB_OK) return rc;
+  if ((rc = tc_forward(net, codes_dev, n, out_dev, s)) != CAB_OK) return rc;
+  return tc_turn_end(net, s);
 }
 
 int cab_eval_f16_dev(cab_net *net, const int8_t *codes_dev, long n, double *out_dev, void *stream) {
@@ -440,7 +476,7 @@ int cab_eval_f16_host(cab_net *net, const int8_t *codes, long n, double *out) {
   CAB_CUDA(cudaSetDevice(net->device));
   int rc = f16_prepare(net, nullptr);
   if (rc != CAB_OK) return rc;
-  F16State *s = static_cast<F16State *>(net->f16);
+  F16State *s = static_cast<F16State *>(net->f16.load(std::memory_order_acquire));
   static std::mutex staging_mu;                  // the staging buffers are per net; host callers take turns
   std::lock_guard<std::mutex> lk(staging_mu);
   if (n > s->cap) {
@@ -462,13 +498,16 @@ int cab_eval_bf16_host(cab_net *net, const int8_t *codes, long n, double *out) {
   if (!net || n < 0 || (n > 0 && (!codes || !out))) { set_error("bad argument"); return CAB_EINVAL; }
   if (n == 0) return CAB_OK;
   CAB_CUDA(cudaSetDevice(net->device));
+  std::lock_guard<std::mutex> turn(net->tc_mu);
   int rc = tc_prepare(net, n, nullptr);
   if (rc != CAB_OK) return rc;
   TcState *s = static_cast<TcState *>(net->tc);
+  if ((rc = tc_turn_begin(net, s->stream)) != CAB_OK) return rc;
   CAB_CUDA(cudaMemcpyAsync(s->d_codes, codes, n * 64, cudaMemcpyHostToDevice, s->stream));
   rc = tc_forward(net, s->d_codes, n, s->d_out, s->stream);
   if (rc != CAB_OK) return rc;
   CAB_CUDA(cudaMemcpyAsync(out, s->d_out, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if ((rc = tc_turn_end(net, s->stream)) != CAB_OK) return rc;
   CAB_CUDA(cudaStreamSynchronize(s->stream));
   return CAB_OK;
 }

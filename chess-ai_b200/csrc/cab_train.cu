@@ -30,13 +30,6 @@ __global__ void __launch_bounds__(256) dropout_kernel(double *__restrict__ w, lo
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(hits, local);
 }
 
-// declared in cab_api.cu
-int ensure_packed(cab_net *net, cudaStream_t stream);
-int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d_out, double *d_save, long save_stride,
-                   cudaStream_t stream);
-struct Geometry { int n_cons, n_stages, ctas_per_sm; };
-Geometry choose_geometry(int a_units, int stage_bytes, long n_boards, int sm_count);
-size_t forward_smem_bytes(int a_units, int n_cons, int n_stages, int stage_bytes);
 
 // ---- NCCL through dlopen: the library must load (and evaluate) on machines without NCCL -------------------------
 struct Id128 { char b[128]; };  // ncclUniqueId: 128 opaque bytes, passed BY VALUE to ncclCommInitRank
@@ -303,6 +296,8 @@ static int fan_out(cab_net *net, cudaStream_t stream, long n, F &&piece) {
 int tc_grad(cab_net *net, const int8_t *d_codes, const double *d_targets, long n, double *d_grad, cudaStream_t stream);
 int tc_forward_out(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream);
 bool tc_fits(const cab_net *net);
+int tc_turn_begin(cab_net *net, cudaStream_t stream);
+int tc_turn_end(cab_net *net, cudaStream_t stream);
 
 static int ensure_tout(cab_net *net, long n) {   // bf16 mode: only the output buffer of the re-forward
   if (n > net->tout_cap) {
@@ -321,12 +316,17 @@ static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d
   if (bf16 && !tc_fits(net)) { set_error("bf16 tcgen05 training needs hidden widths that are multiples of 256"); return CAB_EINVAL; }
   int rc = ensure_train_state(net);
   if (rc != CAB_OK) return rc;
+  std::unique_lock<std::mutex> turn(net->tc_mu, std::defer_lock);
+  if (bf16) {   // the bf16 path's scratch is per net: this step takes its turn (cab_tc.cu)
+    turn.lock();
+    if ((rc = tc_turn_begin(net, stream)) != CAB_OK) return rc;
+  }
   if ((rc = bf16 ? ensure_tout(net, n) : ensure_batch_buffers(net, n)) != CAB_OK) return rc;
   double *d_tout = bf16 ? net->d_tout_tc : net->d_tout;
   const long nw = net->n_weights;
   if (!bf16) {
     std::lock_guard<std::mutex> lk(net->mu);
-    if ((rc = ensure_packed(net, stream)) != CAB_OK) return rc;
+    if ((rc = ensure_packed(net, stream, false)) != CAB_OK) return rc;
   }
   CAB_CUDA(cudaMemsetAsync(net->d_grad, 0, (nw + 4) * sizeof(double), stream));
   set_scalar_kernel<<<1, 1, 0, stream>>>(net->d_grad + nw + 2, (double) n);
@@ -354,7 +354,7 @@ static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d
   } else {
     {
       std::lock_guard<std::mutex> lk(net->mu);
-      if ((rc = ensure_packed(net, stream)) != CAB_OK) return rc;
+      if ((rc = ensure_packed(net, stream, false)) != CAB_OK) return rc;
     }
     rc = fan_out(net, stream, n, [&](long b0, long nb, cudaStream_t s) {
       return launch_forward(net, d_codes + b0 * 64, nb, net->d_tout + b0, nullptr, 0, s);
@@ -387,6 +387,7 @@ static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d
   if (accepted) *accepted = ok ? 1 : 0;
   if (err) *err = e0;
   if (new_err) *new_err = e1;
+  if (bf16 && (rc = tc_turn_end(net, stream)) != CAB_OK) return rc;
   return CAB_OK;
 }
 
@@ -399,8 +400,12 @@ static int train_sequence_impl(cab_net *net, const int8_t *codes, const double *
   cudaStream_t s = net->train_stream;
   CAB_CUDA(cudaMemcpyAsync(net->d_tcodes, codes, n * 64, cudaMemcpyHostToDevice, s));
   CAB_CUDA(cudaMemcpyAsync(net->d_ttargets, targets, n * sizeof(double), cudaMemcpyHostToDevice, s));
-  uint8_t *d_acc = nullptr;
-  CAB_CUDA(cudaMalloc(&d_acc, n));
+  struct DevBytes {   // freed on every return path
+    uint8_t *p = nullptr;
+    ~DevBytes() { cudaFree(p); }
+  } acc_buf;
+  CAB_CUDA(cudaMalloc(&acc_buf.p, n));
+  uint8_t *d_acc = acc_buf.p;
   SeqArgs a{};
   a.w = net->d_w; a.dw = net->d_dw;
   a.codes = net->d_tcodes; a.targets = net->d_ttargets;
@@ -424,7 +429,7 @@ static int train_sequence_impl(cab_net *net, const int8_t *codes, const double *
   a.err_out = net->d_scalars + 10;
   CAB_CUDA(cudaMemcpyAsync(net->d_scalars + 8, lambda, sizeof(double), cudaMemcpyHostToDevice, s));
   const size_t smem = (size_t) 4 * off * sizeof(double);
-  if (smem > 200 * 1024) { cudaFree(d_acc); set_error("network too wide for the sequential trainer"); return CAB_EINVAL; }
+  if (smem > 200 * 1024) { set_error("network too wide for the sequential trainer"); return CAB_EINVAL; }
   CAB_CUDA(cudaFuncSetAttribute(train_sequence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   train_sequence_kernel<<<1, 1024, smem, s>>>(a);
   net->launches++;
@@ -433,7 +438,6 @@ static int train_sequence_impl(cab_net *net, const int8_t *codes, const double *
   CAB_CUDA(cudaMemcpyAsync(h, net->d_scalars + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (accepted_host) CAB_CUDA(cudaMemcpyAsync(accepted_host, d_acc, n, cudaMemcpyDeviceToHost, s));
   CAB_CUDA(cudaStreamSynchronize(s));
-  cudaFree(d_acc);
   *lambda = h[0];
   if (resets) memcpy(resets, &h[1], sizeof(int));
   if (err) *err = h[2];
@@ -544,7 +548,10 @@ int cab_grad_bf16_dev(cab_net *net, const int8_t *codes_dev, const double *targe
   CAB_CUDA(cudaMemsetAsync(net->d_grad, 0, (net->n_weights + 4) * sizeof(double), s));
   set_scalar_kernel<<<1, 1, 0, s>>>(net->d_grad + net->n_weights + 2, (double) n);
   net->launches++;
-  return tc_grad(net, codes_dev, targets_dev, n, net->d_grad, s);
+  std::lock_guard<std::mutex> turn(net->tc_mu);
+  if ((rc = tc_turn_begin(net, s)) != CAB_OK) return rc;
+  if ((rc = tc_grad(net, codes_dev, targets_dev, n, net->d_grad, s)) != CAB_OK) return rc;
+  return tc_turn_end(net, s);
 }
 
 int cab_dp_unique_id(void *id128_out) {

@@ -124,6 +124,24 @@ __device__ __forceinline__ void act_group(double (&acc)[kMaxNBH][2], const doubl
   }
 }
 
+// pre-activations theta of this warp's tiles to global memory, unit layout (K2 with theta export, network.cpp:139-153)
+template <int NBH>
+__device__ __forceinline__ void store_acc_global(const double (&acc)[kMaxNBH][2], double *__restrict__ dst, long stride) {
+#pragma unroll
+  for (int j = 0; j < NBH; ++j) *reinterpret_cast<double2 *>(dst + (size_t) j * stride) = make_double2(acc[j][0], acc[j][1]);
+}
+#define CAB_NB_CASE(N) \
+  case N: store_acc_global<N>(acc, dst, stride); break;
+__device__ __forceinline__ void dispatch_store_global(int nbh, const double (&acc)[kMaxNBH][2], double *dst, long stride) {
+  switch (nbh) {
+    CAB_NB_CASE(1) CAB_NB_CASE(2) CAB_NB_CASE(3) CAB_NB_CASE(4) CAB_NB_CASE(5) CAB_NB_CASE(6) CAB_NB_CASE(7)
+    CAB_NB_CASE(8) CAB_NB_CASE(9) CAB_NB_CASE(10) CAB_NB_CASE(11) CAB_NB_CASE(12) CAB_NB_CASE(13) CAB_NB_CASE(14)
+    CAB_NB_CASE(15) CAB_NB_CASE(16)
+    default: break;
+  }
+}
+#undef CAB_NB_CASE
+
 #define CAB_NB_CASE(N) \
   case N: store_acc<N>(acc, a_out, lane); break;
 __device__ __forceinline__ void dispatch_store(int nbh, const double (&acc)[kMaxNBH][2], double2 *a_out, int lane) {
@@ -161,6 +179,7 @@ struct ForwardArgs {
   const int8_t *codes;      // [n_boards][64]
   double *out;              // [n_boards] or nullptr
   double *save;             // saved activations in unit layout, or nullptr (K2: propagate_for_training)
+  double *save_theta;       // saved PRE-activations theta (network.cpp:150 unbounded[n][j] = sum), same layout; THETA kernels only
   long save_stride;         // doubles per unit row = boards_pad * 8
   int n_stages;             // weight ring depth
   int stage_bytes;          // bytes per ring slot (the plan's chunk size limit)
@@ -178,7 +197,8 @@ __host__ __device__ inline size_t fwd_smem_tail(int n_stages) {
 #define CAB_PROF_ACC(slot, t0) if (PROF) { prof_acc[slot] += clock64() - (t0); }
 
 // JIT = false: f() in an epilogue on each warp's own output tiles (a phase).  JIT = true: f() on the A-operand load.
-template <bool PROF, bool JIT>
+// THETA = true (not JIT): also writes every layer's pre-activations to args.save_theta (K2 as the reference's API returns it).
+template <bool PROF, bool JIT, bool THETA = false>
 __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const ForwardArgs args) {
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CAB_PROF_T(t_kernel)
@@ -299,6 +319,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
         // static register indices; tiles past nbh hold zeros and f(0) = 0. (2) barrier: input fully read.
         // (3) store the activations in place. (4) barrier: outputs visible to the partner.
         double2 *a_out = abuf + (size_t) (d.a_out + j0) * 32;
+        if (THETA && !JIT && args.save_theta != nullptr && valid)
+          dispatch_store_global(nbh, acc, args.save_theta + board0 * 8 + lane * 2 + (size_t) (d.save_off + d.tile0 + j0) * args.save_stride,
+                                args.save_stride);
         if (!JIT) {
           for (int g4 = 0; g4 * 4 < nbh; ++g4) {
             switch (g4) {

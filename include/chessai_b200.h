@@ -20,7 +20,10 @@
  *   - *_host entry points take HOST pointers and include the H2D/D2H copies; *_dev take DEVICE pointers and a
  *     cudaStream_t (passed as void*) and are asynchronous.
  *   - a cab_net is not thread-safe for mutation (train/dropout/set_weights); eval entry points may be called
- *     concurrently from many host threads on one net (mcts_network/tree.cpp:185 does exactly that).
+ *     concurrently from many host threads on one net (mcts_network/tree.cpp:185 does exactly that). The fp64 and
+ *     fused-fp16 evaluators then run concurrently (per-caller scratch); calls of the bf16 wide-net path
+ *     (cab_eval_bf16_*, cab_train_batch_bf16_*, cab_grad_bf16_dev) share per-net scratch and TAKE TURNS: they are
+ *     serialised on the host by a per-net lock and on the device by an event between consecutive calls.
  */
 #ifndef CHESSAI_B200_H_
 #define CHESSAI_B200_H_
@@ -93,6 +96,11 @@ CAB_API int cab_eval_records_host(cab_net *net, const uint8_t *records_host, lon
 /* forward that also returns every layer's activations (Network::propagate_for_training  network.cpp:139-153):
  * acts_host receives n_boards * sum(dims[1..]) doubles, board-major, layers concatenated in order. */
 CAB_API int cab_forward_full_host(cab_net *net, const int8_t *codes_host, long n_boards, double *acts_host);
+/* the same forward returning ALSO the pre-activations theta the reference's second overload fills
+ * (propagate_for_training(unbounded): unbounded[n][j] = sum, network.cpp:139-153), same shape as acts_host
+ * (acts_host may be null). Saturated units keep their true theta (hundreds to thousands with latest.txt). */
+CAB_API int cab_forward_thetas_host(cab_net *net, const int8_t *codes_host, long n_boards, double *acts_host,
+                                    double *thetas_host);
 
 /* ---- MCTS leaf queue with virtual-loss batching (new; sits in front of Decider::prediction, tree.cpp:295) --------- */
 /* Search threads park a playout at an unexpanded node (virtual loss on its path), push the boards they need

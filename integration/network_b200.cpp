@@ -184,14 +184,13 @@ void Network::propagate_for_training(std::vector<std::vector<double>> &unbounded
   for (int i = 0; i < 64; ++i) codes[i] = (int8_t) std::lround(_neurons[0][i] * 2.5);
   long row = 0;
   for (int n = 1; n < _num_layers; ++n) row += _dimensions[n];
-  std::vector<double> acts(row);
-  ck(cab_forward_full_host(side_of(this).handle, codes, 1, acts.data()), "cab_forward_full_host");
+  std::vector<double> acts(row), thetas(row);
+  ck(cab_forward_thetas_host(side_of(this).handle, codes, 1, acts.data(), thetas.data()), "cab_forward_thetas_host");
   long c = 0;
   for (int n = 1; n < _num_layers; ++n)
-    for (int j = 0; j < _dimensions[n]; ++j) {
-      _neurons[n][j] = acts[c++];
-      // theta = f^-1(a) = 4 * atanh(a / 4): the device keeps activations, the pre-activation is recovered on demand
-      unbounded[n][j] = 4.0 * std::atanh(_neurons[n][j] / 4.0);
+    for (int j = 0; j < _dimensions[n]; ++j, ++c) {
+      _neurons[n][j] = acts[c];
+      unbounded[n][j] = thetas[c];   // the sum itself (network.cpp:150), exact also for saturated units
     }
 }
 
@@ -314,27 +313,21 @@ Network *NetworkStorage::current_network() {
   return _current_network;
 }
 
-namespace {
-Network *install(Network *fresh) {
-  return fresh;
-}
-}  // namespace
-
 Network *NetworkStorage::initialize() {
   if (_current_network != nullptr) { DEBUG_ASSERT delete _current_network; }
-  _current_network = install(Network::randomNetwork());
+  _current_network = Network::randomNetwork();
   saveLatestNetwork();
   return _current_network;
 }
 Network *NetworkStorage::initialize(const std::vector<int> &dims) {
   if (_current_network != nullptr) { DEBUG_ASSERT delete _current_network; }
-  _current_network = install(Network::randomNetwork(dims));
+  _current_network = Network::randomNetwork(dims);
   saveLatestNetwork();
   return _current_network;
 }
 Network *NetworkStorage::initialize(const std::string &file_path) {
   if (_current_network != nullptr) { DEBUG_ASSERT delete _current_network; }
-  _current_network = install(Network::loadFromFile(file_path));
+  _current_network = Network::loadFromFile(file_path);
   saveLatestNetwork();
   return _current_network;
 }

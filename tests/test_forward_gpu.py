@@ -117,6 +117,25 @@ def test_forward_full_matches_oracle_activations(cab, port, net, golden):
         assert np.abs(acts[b] - want).max() < 1e-9  # activations live in (-4, 4)
 
 
+def test_forward_thetas_match_oracle_preactivations(cab, port, net, golden):
+    # K2 as the reference's API returns it: propagate_for_training(unbounded) fills unbounded[n][j] = sum
+    # (network.cpp:139-153). latest.txt saturates most hidden units (|theta| up to thousands), where f^-1(a) is +-inf:
+    # the device must hand back the sums themselves.
+    pn = port.net_from_weights(DEFAULT_DIMS, golden["latest_weights"])
+    codes = np.concatenate([golden["syn_codes"][:40], golden["case_codes"][:26]])
+    acts, thetas = net.forward_thetas(codes)
+    assert np.isfinite(thetas).all()
+    saturated = 0
+    for b in range(len(codes)):
+        ne, th = pn.forward_full(codes[b])
+        assert np.abs(acts[b] - ne[64:]).max() < 1e-9
+        want = th[64:]
+        assert (np.abs(thetas[b] - want) <= 1e-11 * np.maximum(1.0, np.abs(want))).all()
+        saturated += int((np.abs(want) > 80).sum())
+    assert saturated > 0.5 * thetas.size          # the case the atanh reconstruction could not serve
+    assert np.array_equal(acts, net.forward_full(codes))
+
+
 def test_saturated_inputs_give_exact_bounds(cab):
     # exp overflow -> exactly +-4: huge weights drive every unit into saturation, no NaN
     dims = [64, 16, 1]

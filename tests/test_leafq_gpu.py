@@ -21,6 +21,50 @@ pytestmark = pytest.mark.gpu
 BIN = os.path.join(ROOT, "integration", "_build", "batched_mcts")
 
 
+def test_leaf_queue_near_capacity_pushes_never_share_a_slot(cab, golden):
+    # many threads racing for the last slots: every successful reservation is disjoint, failures leave no hole,
+    # pending never exceeds the capacity (the reservation is a compare-and-swap, not fetch_add + fetch_sub)
+    net = cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"])
+    lib = cab.lib()
+    cap = 1000
+    for _ in range(20):
+        q = C.c_void_p(None)
+        cab._ck(lib.cab_leafq_create(net._h, cap, 4096, 2, C.byref(q)))
+        first = C.c_long(-1)
+        filler = np.zeros((cap - 37, 64), dtype=np.int8)
+        cab._ck(lib.cab_leafq_push(q, filler.reshape(-1), cap - 37, C.byref(first)))
+        got, over = [], []
+
+        def worker(t):
+            rng = np.random.default_rng(t)
+            for _ in range(40):
+                n = int(rng.integers(1, 12))
+                slot = C.c_long(-1)
+                rc = lib.cab_leafq_push(q, np.full((n, 64), t + 1, dtype=np.int8).reshape(-1), n, C.byref(slot))
+                if rc == 0:
+                    got.append((slot.value, n))
+                else:
+                    assert rc == cab.CAB_ESTATE
+                pend = C.c_long(0)
+                lib.cab_leafq_pending(q, C.byref(pend))
+                over.append(pend.value)
+
+        ts = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert max(over) <= cap
+        got.sort()
+        at = cap - 37
+        for slot, n in got:                      # contiguous, disjoint, in order of reservation
+            assert slot == at
+            at += n
+        assert at <= cap
+        pend = C.c_long(0)
+        cab._ck(lib.cab_leafq_pending(q, C.byref(pend)))
+        assert pend.value == at
+        cab._ck(lib.cab_leafq_destroy(q))
+
+
 def test_leaf_queue_from_threads_matches_batched_eval(cab, golden):
     net = cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"])
     lib = cab.lib()
