@@ -62,6 +62,11 @@ def build(verbose=False, force=False):
     if force or _stale(tr, tr_deps):
         subprocess.check_call([gxx, "-std=c++17", "-O2", "-static-libstdc++", "-static-libgcc", "-o", tr, tr_deps[0],
                                "-L" + LIB_DIR, "-lchessai_b200", "-Wl,-rpath,$ORIGIN"])
+    fb = os.path.join(LIB_DIR, "fwd_bench")      # native timing harness of the forward path (kernel-variant sweeps)
+    fb_src = os.path.join(CSRC, "tools", "fwd_bench.cpp")
+    if force or _stale(fb, [fb_src, LIB]):
+        subprocess.check_call([gxx, "-std=c++17", "-O2", "-static-libstdc++", "-static-libgcc", "-I/usr/local/cuda/include", "-o", fb, fb_src,
+                               "-L" + LIB_DIR, "-lchessai_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN"])
     for name in ("pipe_peaks", "tma_stream"):      # microbenchmarks behind the roofline denominators / design choices
         tool = os.path.join(LIB_DIR, name)
         tsrc = os.path.join(CSRC, "tools", name + ".cu")

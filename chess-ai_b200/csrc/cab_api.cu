@@ -195,7 +195,6 @@ static void build_plan(const cab_net *net, bool transposed, StreamPlan *plan) {
         d.n_tiles = (uint16_t) n_tiles;
         d.save_off = transposed ? net->act_unit_off[l] : net->act_unit_off[l + 1];
         d.save_in = transposed ? net->act_unit_off[l + 1] : net->act_unit_off[l];
-        if (!transposed && l > 0) d.flags |= kActIn;  // the layer input holds pre-activations when the JIT kernel runs
         plan->chunks.push_back(d);
       }
       off += sg.n_doubles;
@@ -210,6 +209,13 @@ static int upload_plan(StreamPlan *plan) {
   if (plan->total_doubles == 0) return CAB_OK;
   CAB_CUDA(cudaMalloc(&plan->d_chunks, plan->chunks.size() * sizeof(ChunkDesc)));
   CAB_CUDA(cudaMemcpy(plan->d_chunks, plan->chunks.data(), plan->chunks.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice));
+  {  // the kernel's start-up tables in one piece: the first kSmemChunks descriptors, then the exp table (the device's own copy)
+    std::vector<uint8_t> blob(kBlobBytes, 0);
+    memcpy(blob.data(), plan->chunks.data(), std::min(plan->chunks.size(), (size_t) kSmemChunks) * sizeof(ChunkDesc));
+    CAB_CUDA(cudaMemcpyFromSymbol(blob.data() + kBlobChunkBytes, c_exp2_tbl, kExpTblSize * sizeof(double)));
+    CAB_CUDA(cudaMalloc(&plan->d_blob, kBlobBytes));
+    CAB_CUDA(cudaMemcpy(plan->d_blob, blob.data(), kBlobBytes, cudaMemcpyHostToDevice));
+  }
   CAB_CUDA(cudaMalloc(&plan->d_segs, plan->segs.size() * sizeof(PackSeg)));
   CAB_CUDA(cudaMemcpy(plan->d_segs, plan->segs.data(), plan->segs.size() * sizeof(PackSeg), cudaMemcpyHostToDevice));
   CAB_CUDA(cudaMalloc(&plan->d_pack, plan->total_doubles * sizeof(double)));
@@ -217,8 +223,8 @@ static int upload_plan(StreamPlan *plan) {
 }
 
 static void free_plan(StreamPlan *plan) {
-  cudaFree(plan->d_chunks); cudaFree(plan->d_segs); cudaFree(plan->d_pack);
-  plan->d_chunks = nullptr; plan->d_segs = nullptr; plan->d_pack = nullptr;
+  cudaFree(plan->d_chunks); cudaFree(plan->d_segs); cudaFree(plan->d_pack); cudaFree(plan->d_blob);
+  plan->d_chunks = nullptr; plan->d_segs = nullptr; plan->d_pack = nullptr; plan->d_blob = nullptr;
 }
 
 size_t forward_smem_bytes(int a_units, int n_cons, int n_stages, int stage_bytes) {
@@ -228,17 +234,22 @@ size_t forward_smem_bytes(int a_units, int n_cons, int n_stages, int stage_bytes
 void tc_free(cab_net *net);  // cab_tc.cu
 
 constexpr size_t kSmemMax = 227 * 1024;
-constexpr bool kDefaultJit = false;  // activation applied just-in-time on the A-operand load (see mlp_stream_kernel.cuh)
+constexpr int kDefaultTeamShift = 3, kDefaultTeamLag = 0;   // teams of 8 warps; lag in cycles per team index
 
 // CTA geometry: warp PAIRS per CTA (8 boards each), weight-ring depth, CTAs per SM. Wide layers trade pairs for
 // activation space. n_cons counts pairs. CAB_FWD_PAIRS / CAB_FWD_STAGES override for experiments.
+// n_boards > 0: the launch runs ALONE on the device (the caller serialises its launches), so it is spread over as many
+// SMs as possible: pairs per CTA = ceil(8-board tiles / SMs). n_boards = 0: throughput geometry (other launches overlap).
 Geometry choose_geometry(int a_units, int stage_bytes, long n_boards, int sm_count) {
   static const int env_w = getenv("CAB_FWD_PAIRS") ? atoi(getenv("CAB_FWD_PAIRS")) : 0;
   static const int env_s = getenv("CAB_FWD_STAGES") ? atoi(getenv("CAB_FWD_STAGES")) : 0;
-  (void) n_boards; (void) sm_count;
   Geometry g{0, 0, 1};
   const int max_pairs = kConsumerWarps / 2;
-  const int want = env_w > 0 ? std::min(env_w, max_pairs) : max_pairs;
+  int want = env_w > 0 ? std::min(env_w, max_pairs) : max_pairs;
+  if (env_w <= 0 && n_boards > 0) {
+    const long tiles = (n_boards + kBoardsPerWarp - 1) / kBoardsPerWarp;
+    want = (int) std::max<long>(1, std::min<long>(max_pairs, (tiles + sm_count - 1) / sm_count));
+  }
   for (int p = want; p >= 1; --p) {
     if (forward_smem_bytes(a_units, p, 2, stage_bytes) > kSmemMax) continue;
     g.n_cons = p;
@@ -254,6 +265,15 @@ Geometry choose_geometry(int a_units, int stage_bytes, long n_boards, int sm_cou
   return g;
 }
 int consumer_warps_for(int a_units, int stage_bytes) { return choose_geometry(a_units, stage_bytes, 0, 148).n_cons; }
+
+// stagger of the warp teams inside a CTA (mlp_stream_kernel.cuh): cycles of delay per team index, teams = warp >> shift
+static void team_stagger(int n_pairs, int *shift, int *lag) {
+  static const int env_lag = getenv("CAB_FWD_LAG") ? atoi(getenv("CAB_FWD_LAG")) : -1;
+  static const int env_shift = getenv("CAB_FWD_TEAM_SHIFT") ? atoi(getenv("CAB_FWD_TEAM_SHIFT")) : -1;
+  *shift = env_shift >= 1 ? env_shift : kDefaultTeamShift;
+  *lag = env_lag >= 0 ? env_lag : kDefaultTeamLag;
+  if ((2 * n_pairs) >> *shift < 2) *lag = 0;   // a single team: nothing to stagger
+}
 
 // (re)build the packed streams from d_w on `stream`. Call with net->mu held. drain = true waits for the pack kernels
 // before the flag falls, so evaluations on OTHER streams may follow; drain = false is for callers whose next launches
@@ -273,7 +293,7 @@ int ensure_packed(cab_net *net, cudaStream_t stream, bool drain) {
 }
 
 int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d_out, double *d_save, long save_stride,
-                   cudaStream_t stream, double *d_theta) {
+                   cudaStream_t stream, double *d_theta, bool alone) {
   if (n_boards <= 0) return CAB_OK;
   if (!net->fp64_ok) {
     set_error("layer too wide for the fp64 stream kernel (%d activation units per pair exceed shared memory); "
@@ -286,9 +306,10 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
   a.n_chunks = (int) net->fwd.chunks.size();
   a.a_units = net->fwd.a_units;
   a.n_boards = n_boards;
-  const Geometry geo = choose_geometry(a.a_units, net->stage_bytes, n_boards, net->sm_count);
+  const Geometry geo = choose_geometry(a.a_units, net->stage_bytes, alone ? n_boards : 0, net->sm_count);
   a.stage_bytes = net->stage_bytes;
   const int n_cons = geo.n_cons;
+  team_stagger(n_cons, &a.team_shift, &a.team_lag);
   a.n_stages = geo.n_stages;
   const int boards_per_cta = n_cons * kBoardsPerWarp;
   a.n_groups = (n_boards + boards_per_cta - 1) / boards_per_cta;
@@ -297,10 +318,16 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
   a.save = d_save;
   a.save_theta = d_theta;
   a.save_stride = save_stride;
+  a.blob = net->fwd.d_blob;
+  for (int st = 0; st < geo.n_stages && st < kMaxStages; ++st) {   // the ring's first fills, as kernel parameters
+    const ChunkDesc &cd = net->fwd.chunks[st % net->fwd.chunks.size()];
+    a.fill_off[st] = cd.src_off;
+    a.fill_bytes[st] = cd.bytes;
+  }
+  if (reinterpret_cast<uintptr_t>(d_codes) & 1) { set_error("board codes must be 2-byte aligned"); return CAB_EINVAL; }
   const size_t smem = forward_smem_bytes(a.a_units, n_cons, geo.n_stages, net->stage_bytes);
   const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * geo.ctas_per_sm);
   static const bool prof_env = getenv("CAB_FWD_PROFILE") != nullptr;
-  static const bool jit = getenv("CAB_FWD_JIT") ? atoi(getenv("CAB_FWD_JIT")) != 0 : kDefaultJit;
   if (prof_env) {
     // debug: per-warp phase cycle counters of ONE launch, printed to stderr (never on by default)
     long long *d_prof = nullptr;
@@ -308,10 +335,8 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
     CAB_CUDA(cudaMalloc(&d_prof, nw * 8 * sizeof(long long)));
     CAB_CUDA(cudaMemset(d_prof, 0, nw * 8 * sizeof(long long)));
     a.prof = d_prof;
-    CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (jit) mlp_forward_kernel<true, true><<<grid, n_cons * 64, smem, stream>>>(a);
-    else mlp_forward_kernel<true, false><<<grid, n_cons * 64, smem, stream>>>(a);
+    CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    mlp_forward_kernel<true><<<grid, n_cons * 64, smem, stream>>>(a);
     CAB_CUDA(cudaStreamSynchronize(stream));
     std::vector<long long> h(nw * 8);
     CAB_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -324,9 +349,8 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
     net->launches++;
     return CAB_OK;
   }
-  if (d_theta != nullptr) mlp_forward_kernel<false, false, true><<<grid, n_cons * 64, smem, stream>>>(a);
-  else if (jit) mlp_forward_kernel<false, true><<<grid, n_cons * 64, smem, stream>>>(a);
-  else mlp_forward_kernel<false, false><<<grid, n_cons * 64, smem, stream>>>(a);
+  if (d_theta != nullptr) mlp_forward_kernel<false, true><<<grid, n_cons * 64, smem, stream>>>(a);
+  else mlp_forward_kernel<false><<<grid, n_cons * 64, smem, stream>>>(a);
   net->launches++;
   CAB_CUDA(cudaGetLastError());
   return CAB_OK;
@@ -388,9 +412,8 @@ static int init_net(cab_net *net, const std::vector<int> &dims, int device) {
   // very wide layers do not fit the fp64 stream kernel's per-pair activation buffer: the network is still usable
   // through the bf16 tcgen05 path (cab_eval_bf16_*); the fp64 entry points then return CAB_EINVAL
   net->fp64_ok = consumer_warps_for(std::max(net->fwd.a_units, net->bwd.a_units), net->stage_bytes) > 0;
-  CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   return CAB_OK;
 }
@@ -688,7 +711,8 @@ int cab_eval_dev(cab_net *net, const int8_t *codes_dev, long n, double *out_dev,
     std::lock_guard<std::mutex> lk(net->mu);
     if ((rc = ensure_packed(net, (cudaStream_t) stream, true)) != CAB_OK) return rc;  // other streams may evaluate next
   }
-  return launch_forward(net, codes_dev, n, out_dev, nullptr, 0, (cudaStream_t) stream);
+  // one launch on the caller's stream: spread it over the whole device (latency geometry)
+  return launch_forward(net, codes_dev, n, out_dev, nullptr, 0, (cudaStream_t) stream, nullptr, /*alone=*/true);
 }
 
 int cab_eval_dev_batches(cab_net *net, const int8_t *codes_dev, long n, long batch, double *out_dev,
@@ -705,8 +729,9 @@ int cab_eval_dev_batches(cab_net *net, const int8_t *codes_dev, long n, long bat
   }
   int i = 0;
   for (long b0 = 0; b0 < n; b0 += batch, ++i) {
+    // a single stream serialises the launches, each then has the device to itself: latency geometry
     rc = launch_forward(net, codes_dev + b0 * 64, std::min(batch, n - b0), out_dev + b0, nullptr, 0,
-                        (cudaStream_t) streams[i % n_streams]);
+                        (cudaStream_t) streams[i % n_streams], nullptr, /*alone=*/n_streams == 1);
     if (rc != CAB_OK) return rc;
   }
   return CAB_OK;

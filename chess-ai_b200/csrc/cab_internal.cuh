@@ -65,6 +65,7 @@ struct StreamPlan {  // host description of one packed stream
   long total_doubles = 0;
   int a_units = 0;      // per-warp activation buffer size in units
   ChunkDesc *d_chunks = nullptr;
+  uint8_t *d_blob = nullptr;  // [ChunkDesc x kSmemChunks][exp table]: what the forward kernel copies to shared memory at start
   PackSeg *d_segs = nullptr;
   double *d_pack = nullptr;
 };
@@ -136,7 +137,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 // cab_api.cu, used by the other translation units
 int ensure_packed(cab_net *net, cudaStream_t stream, bool drain);
 int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d_out, double *d_save, long save_stride,
-                   cudaStream_t stream, double *d_theta = nullptr);
+                   cudaStream_t stream, double *d_theta = nullptr, bool alone = false);
 struct Geometry { int n_cons, n_stages, ctas_per_sm; };
 Geometry choose_geometry(int a_units, int stage_bytes, long n_boards, int sm_count);
 size_t forward_smem_bytes(int a_units, int n_cons, int n_stages, int stage_bytes);
@@ -305,20 +306,25 @@ static __constant__ double c_exp2_tbl[256] = {
 constexpr int kExpTblSize = 256;
 
 // act_f with a table-driven exp, arranged for the FEWEST fp64-pipe operations (the pipe is shared with the DMMAs, so
-// every activation operation is a DMMA slot lost: measured, the activation costs 13 % of the kernel's throughput):
+// every activation operation is a DMMA slot lost):
 //   t = -x/2 = (256 k + j) ln2/256 + r,  |r| <= ln2/512;  exp(t) = 2^k T[j] exp(r),  T[j] = 2^(j/256)
+//   * the saturation clamp |x| <= 120 (exp(+-60) already gives f = -+4 exactly like the reference's inf / 0 path) is
+//     done on the INTEGER pipe, on the high word of x (also catches inf and NaN)
 //   * the kernel works with r' = -2 r = x + n (ln2/128), so t itself is never formed
-//   * exp(r) = 1 + r' q(r'), q of degree 3 (truncation r^5/120 < 3.8e-17)
-//   * d8 = (1 + exp(t)) / 8 = (1/8 + T8) + (T8 r') q with T8 = 2^(k-3) T[j] (exponent arithmetic on the integer pipe)
+//   * exp(r) = p = 1 + r' q(r'), q of degree 3 (truncation r^5/120 < 3.8e-17)
+//   * d8 = (1 + exp(t)) / 8 = 1/8 + T8 p with T8 = 2^(k-3) T[j] (exponent arithmetic on the integer pipe): ONE fma,
+//     the product exact inside it
 //   * 8 / (1 + exp(t)) = 1 / d8 by MUFU.RCP64H (relative error 9.3e-7) and ONE cubic step y (1 + e + e^2), e = 1 - d8 y
 //     (residual e^3 < 1e-18);  f = 8 / (1 + exp(t)) - 4
-// 16 fp64-pipe operations (20 before). `tbl` is the shared-memory copy of c_exp2_tbl.
+// 13 fp64-pipe operations (round 1: 16; the libm expression: ~51 lane-clocks). `tbl` is the shared-memory copy of c_exp2_tbl.
 __device__ __forceinline__ double act_f_tbl(double x, const double *tbl) {
-  const double xc = fmin(fmax(x, -120.0), 120.0);          // exp(+-60) already saturates f to +-4 exactly like the reference
+  const int hx = __double2hiint(x);
+  const bool big = (unsigned) (hx & 0x7fffffff) >= 0x405e0000u;           // |x| >= 120.0 (0x405E000000000000), inf, NaN
+  const double xc = __hiloint2double(big ? ((hx & (int) 0x80000000) | 0x405e0000) : hx, big ? 0 : __double2loint(x));
   const double magic = 6755399441055744.0;
   const double nm = fma(xc, -184.66496523378732, magic);   // n = rint(-x/2 * 256/ln2)
   const double nd = nm - magic;
-  double r = fma(nd, 0.00541521234663378, xc);          // r' = x + n * ln2_hi/128   (fdlibm's split of ln 2, scaled exactly)
+  double r = fma(nd, 0.00541521234663378, xc);              // r' = x + n * ln2_hi/128   (fdlibm's split of ln 2, scaled exactly)
   r = fma(nd, 1.4907929134926466e-12, r);                   //        + n * ln2_lo/128
   const int ki = __double2loint(nm);
   const double tj = tbl[ki & 255];
@@ -326,7 +332,8 @@ __device__ __forceinline__ double act_f_tbl(double x, const double *tbl) {
   double q = fma(r, 2.6041666666666665e-03, -2.0833333333333332e-02);   // 1/384, -1/48
   q = fma(r, q, 0.125);
   q = fma(r, q, -0.5);
-  const double d8 = fma(t8 * r, q, 0.125 + t8);
+  const double pe = fma(r, q, 1.0);
+  const double d8 = fma(t8, pe, 0.125);
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d8));
   const double e = fma(-d8, y, 1.0);

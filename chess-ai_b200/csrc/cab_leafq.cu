@@ -148,7 +148,8 @@ int cab_leafq_flush_async(cab_leafq *q, long *n_evaluated) {
     const long nb = std::min(q->batch, n - b0);
     cudaStream_t s = q->streams[i % q->n_streams];
     CAB_CUDA(cudaMemcpyAsync(q->d_codes + b0 * 64, q->h_codes + b0 * 64, nb * 64, cudaMemcpyHostToDevice, s));
-    int rc = launch_forward(net, q->d_codes + b0 * 64, nb, q->d_out + b0, nullptr, 0, s);
+    // search threads wait for this flush: spread every launch over the whole device (latency geometry)
+    int rc = launch_forward(net, q->d_codes + b0 * 64, nb, q->d_out + b0, nullptr, 0, s, nullptr, /*alone=*/true);
     if (rc != CAB_OK) return rc;
     CAB_CUDA(cudaMemcpyAsync(q->h_out + b0, q->d_out + b0, nb * sizeof(double), cudaMemcpyDeviceToHost, s));
     ++q->launches;

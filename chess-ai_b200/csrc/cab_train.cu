@@ -209,7 +209,7 @@ static int launch_backward(cab_net *net, const double *d_targets, long b0, long 
   a.n_chunks = (int) net->bwd.chunks.size();
   a.a_units = net->bwd.a_units;
   a.n_boards = n;
-  const Geometry geo = choose_geometry(a.a_units, net->stage_bytes, n, net->sm_count);
+  const Geometry geo = choose_geometry(a.a_units, net->stage_bytes, 0, net->sm_count);
   a.n_stages = geo.n_stages;
   a.stage_bytes = net->stage_bytes;
   const int boards_per_cta = geo.n_cons * kBoardsPerWarp;

@@ -14,6 +14,8 @@
 //   * the DMMA C-fragment of tile j IS the A-fragment pair of the next layer's k-steps (2j, 2j+1) under the feature
 //     permutation k = 8t + 2q + h that the packed stream bakes in, so activations never change layout
 //   * persistent grid: CTAs loop over board groups; the weight stream is re-read from L2 per group
+//   * a CTA of a 4096-board launch lives for one pass: its start-up (input codes requested first, tables by one bulk
+//     copy, first ring fills from kernel parameters) is trimmed like an inner loop
 #pragma once
 #include "cab_internal.cuh"
 
@@ -34,30 +36,14 @@ __device__ __forceinline__ void pair_barrier(int pair) {  // named barrier 1 + p
   asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
 }
 
-// A-operand load of one input unit. ACT (just-in-time activation): the unit still holds the previous layer's
-// pre-activations theta; f() is applied here, one input unit ahead of its use, so the exp / reciprocal chain overlaps
-// the DMMA issue of the current unit instead of forming a phase of its own. Both warps of a pair do this redundantly
-// (each needs every input unit); nothing is written back.
-template <bool ACT>
-__device__ __forceinline__ double2 load_a(uint32_t addr, const double *tbl, double *save_row) {
-  double2 a = lds_frag(addr);
-  if (ACT) {
-    a.x = act_f_tbl(a.x, tbl);
-    a.y = act_f_tbl(a.y, tbl);
-    if (save_row != nullptr) *reinterpret_cast<double2 *>(save_row) = a;
-  }
-  return a;
-}
-
 // One chunk = tcount input units x NBH output tiles of this warp's half. B fragments are fetched one group of kG
 // tiles ahead (across the t boundary too); inside a group the kG ".x" DMMAs are issued before the dependent ".y" ones.
 constexpr int kG = 2;
-template <int NBH, bool ACT>
-__device__ __forceinline__ void run_chunk(double (&acc)[kMaxNBH][2], uint32_t a_addr, uint32_t w_addr, uint32_t t_stride,
-                                          int tcount, const double *tbl, double *save_row, long save_stride) {
+template <int NBH>
+__device__ __forceinline__ void run_chunk(double (&acc)[kMaxNBH][2], uint32_t a_addr, uint32_t w_addr, uint32_t t_stride, int tcount) {
   constexpr int NG = (NBH + kG - 1) / kG;
   double2 bcur[kG], bnxt[kG];
-  double2 a = load_a<ACT>(a_addr, tbl, save_row);
+  double2 a = lds_frag(a_addr);
 #pragma unroll
   for (int i = 0; i < kG; ++i)
     if (i < NBH) bcur[i] = lds_frag(w_addr + i * kUnitBytes);
@@ -65,9 +51,7 @@ __device__ __forceinline__ void run_chunk(double (&acc)[kMaxNBH][2], uint32_t a_
     const uint32_t wt = w_addr + (uint32_t) t * t_stride;
     const bool more = t + 1 < tcount;
     double2 a_next = a;
-    if (more)
-      a_next = load_a<ACT>(a_addr + (uint32_t) (t + 1) * kUnitBytes, tbl,
-                           save_row != nullptr ? save_row + (size_t) (t + 1) * save_stride : nullptr);
+    if (more) a_next = lds_frag(a_addr + (uint32_t) (t + 1) * kUnitBytes);
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       if (g + 1 < NG) {
@@ -98,14 +82,10 @@ __device__ __forceinline__ void store_acc(const double (&acc)[kMaxNBH][2], doubl
   for (int j = 0; j < NBH; ++j) a_out[j * 32 + lane] = make_double2(acc[j][0], acc[j][1]);
 }
 
-#define CAB_NB_CASE(N)                                                                                     \
-  case N:                                                                                                  \
-    if (act_in) run_chunk<N, true>(acc, a_addr, w_addr, t_stride, tcount, tbl, save_row, save_stride);     \
-    else run_chunk<N, false>(acc, a_addr, w_addr, t_stride, tcount, nullptr, nullptr, 0);                  \
-    break;
-__device__ __forceinline__ void dispatch_chunk(int nbh, bool act_in, double (&acc)[kMaxNBH][2], uint32_t a_addr,
-                                               uint32_t w_addr, uint32_t t_stride, int tcount, const double *tbl,
-                                               double *save_row, long save_stride) {
+#define CAB_NB_CASE(N) \
+  case N: run_chunk<N>(acc, a_addr, w_addr, t_stride, tcount); break;
+__device__ __forceinline__ void dispatch_chunk(int nbh, double (&acc)[kMaxNBH][2], uint32_t a_addr, uint32_t w_addr,
+                                               uint32_t t_stride, int tcount) {
   switch (nbh) {
     CAB_NB_CASE(1) CAB_NB_CASE(2) CAB_NB_CASE(3) CAB_NB_CASE(4) CAB_NB_CASE(5) CAB_NB_CASE(6) CAB_NB_CASE(7)
     CAB_NB_CASE(8) CAB_NB_CASE(9) CAB_NB_CASE(10) CAB_NB_CASE(11) CAB_NB_CASE(12) CAB_NB_CASE(13) CAB_NB_CASE(14)
@@ -114,13 +94,39 @@ __device__ __forceinline__ void dispatch_chunk(int nbh, bool act_in, double (&ac
   }
 }
 #undef CAB_NB_CASE
-// f() on accumulator tiles 4G .. 4G+3 in place (8 independent activations in flight per lane)
-template <int G>
-__device__ __forceinline__ void act_group(double (&acc)[kMaxNBH][2], const double *tbl) {
+// f() on accumulator tiles T0 .. T0+NT-1 in place (2 NT independent activations in flight per lane)
+template <int T0, int NT>
+__device__ __forceinline__ void act_tiles(double (&acc)[kMaxNBH][2], const double *tbl) {
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    acc[4 * G + u][0] = act_f_tbl(acc[4 * G + u][0], tbl);
-    acc[4 * G + u][1] = act_f_tbl(acc[4 * G + u][1], tbl);
+  for (int u = 0; u < NT; ++u) {
+    acc[T0 + u][0] = act_f_tbl(acc[T0 + u][0], tbl);
+    acc[T0 + u][1] = act_f_tbl(acc[T0 + u][1], tbl);
+  }
+}
+// f() on this warp's nbh tiles, four tiles (eight activations in flight) at a time and EXACTLY nbh of them: the
+// activation shares the fp64 pipe with the DMMAs, a padded tile costs as much as a real one. The switch gives the
+// rolled loop static register indices.
+__device__ __forceinline__ void act_all(int nbh, double (&acc)[kMaxNBH][2], const double *tbl) {
+  for (int t0 = 0; t0 < nbh; t0 += 4) {
+    const int nt = nbh - t0 < 4 ? nbh - t0 : 4;
+    switch (t0 + nt - 1) {
+      case 0: act_tiles<0, 1>(acc, tbl); break;
+      case 1: act_tiles<0, 2>(acc, tbl); break;
+      case 2: act_tiles<0, 3>(acc, tbl); break;
+      case 3: act_tiles<0, 4>(acc, tbl); break;
+      case 4: act_tiles<4, 1>(acc, tbl); break;
+      case 5: act_tiles<4, 2>(acc, tbl); break;
+      case 6: act_tiles<4, 3>(acc, tbl); break;
+      case 7: act_tiles<4, 4>(acc, tbl); break;
+      case 8: act_tiles<8, 1>(acc, tbl); break;
+      case 9: act_tiles<8, 2>(acc, tbl); break;
+      case 10: act_tiles<8, 3>(acc, tbl); break;
+      case 11: act_tiles<8, 4>(acc, tbl); break;
+      case 12: act_tiles<12, 1>(acc, tbl); break;
+      case 13: act_tiles<12, 2>(acc, tbl); break;
+      case 14: act_tiles<12, 3>(acc, tbl); break;
+      default: act_tiles<12, 4>(acc, tbl); break;
+    }
   }
 }
 
@@ -176,7 +182,7 @@ struct ForwardArgs {
   int a_units;              // per-pair activation buffer, in units
   long n_boards;
   long n_groups;            // ceil(n_boards / (8 * pairs per CTA))
-  const int8_t *codes;      // [n_boards][64]
+  const int8_t *codes;      // [n_boards][64], 2-byte aligned
   double *out;              // [n_boards] or nullptr
   double *save;             // saved activations in unit layout, or nullptr (K2: propagate_for_training)
   double *save_theta;       // saved PRE-activations theta (network.cpp:150 unbounded[n][j] = sum), same layout; THETA kernels only
@@ -184,21 +190,41 @@ struct ForwardArgs {
   int n_stages;             // weight ring depth
   int stage_bytes;          // bytes per ring slot (the plan's chunk size limit)
   long long *prof;          // optional [n_warps_total][8] phase cycle counters (CAB_FWD_PROFILE debug launches)
+  int team_shift;           // warps >> team_shift = team; team k starts k * team_lag cycles late (0 lag: lock-step)
+  int team_lag;
+  const uint8_t *blob;      // [ChunkDesc x kSmemChunks][exp table]: the kernel's tables, fetched by ONE bulk copy
+  uint32_t fill_off[kMaxStages], fill_bytes[kMaxStages];   // the first n_stages chunks (kernel parameters: no global read before the first fetch)
 };
 
 // shared memory carve-up, in this order
 __host__ __device__ inline size_t fwd_smem_ring(int n_stages, int stage_bytes) { return (size_t) n_stages * stage_bytes; }
 __host__ __device__ inline size_t fwd_smem_abuf(int n_pairs, int a_units) { return (size_t) n_pairs * a_units * kUnitBytes; }
+constexpr size_t kBlobChunkBytes = (size_t) kSmemChunks * sizeof(ChunkDesc), kBlobBytes = kBlobChunkBytes + kExpTblSize * sizeof(double);
 __host__ __device__ inline size_t fwd_smem_tail(int n_stages) {
-  return (size_t) kSmemChunks * sizeof(ChunkDesc) + kExpTblSize * sizeof(double) + (size_t) n_stages * (sizeof(uint64_t) + sizeof(uint32_t)) + 16;
+  return kBlobBytes + (size_t) (n_stages + 1) * sizeof(uint64_t) + (size_t) n_stages * sizeof(uint32_t) + 16;
 }
 
 #define CAB_PROF_T(var) long long var = 0; if (PROF) var = clock64();
 #define CAB_PROF_ACC(slot, t0) if (PROF) { prof_acc[slot] += clock64() - (t0); }
 
-// JIT = false: f() in an epilogue on each warp's own output tiles (a phase).  JIT = true: f() on the A-operand load.
-// THETA = true (not JIT): also writes every layer's pre-activations to args.save_theta (K2 as the reference's API returns it).
-template <bool PROF, bool JIT, bool THETA = false>
+// the input codes of one lane for one board group: 4 x 2 bytes (units 2 tt + half, features 2q, 2q+1 of board m)
+struct LaneCodes { uint32_t v[2]; };   // bytes: unit half+0: (c0, c1), half+2: (c0, c1) | half+4, half+6
+__device__ __forceinline__ LaneCodes load_codes(const int8_t *codes, long board, bool valid, int half, int q) {
+  LaneCodes c;
+  const int8_t *row = codes + (valid ? board : 0) * 64;
+  uint32_t w[4];
+#pragma unroll
+  for (int tt = 0; tt < 4; ++tt) {
+    w[tt] = 0;
+    if (valid) w[tt] = __ldg(reinterpret_cast<const uint16_t *>(row + 8 * (2 * tt + half) + 2 * q));
+  }
+  c.v[0] = w[0] | (w[1] << 16);
+  c.v[1] = w[2] | (w[3] << 16);
+  return c;
+}
+
+// THETA = true: also writes every layer's pre-activations to args.save_theta (K2 as the reference's API returns it).
+template <bool PROF, bool THETA = false>
 __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const ForwardArgs args) {
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CAB_PROF_T(t_kernel)
@@ -210,38 +236,46 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
   ChunkDesc *s_chunks = reinterpret_cast<ChunkDesc *>(smem + fwd_smem_ring(n_stages, stage_bytes) + fwd_smem_abuf(n_pairs, args.a_units));
   double *exp_tbl = reinterpret_cast<double *>(s_chunks + kSmemChunks);  // 2^(j/256) for the table-driven exp
   uint64_t *full = reinterpret_cast<uint64_t *>(exp_tbl + kExpTblSize);
-  uint32_t *done = reinterpret_cast<uint32_t *>(full + n_stages);  // arrivals per ring slot, monotonically increasing
+  uint64_t *tbl_bar = full + n_stages;                                   // completes when the tables have landed
+  uint32_t *done = reinterpret_cast<uint32_t *>(tbl_bar + 1);            // arrivals per ring slot, monotonically increasing
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = warp >> 1, half = pair_half(warp);
+  const int m = lane >> 2, q = lane & 3;
   // chunks this CTA will consume, in order: (groups it owns) x n_chunks
   const long my_groups = args.n_groups > blockIdx.x ? (args.n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long total_chunks = my_groups * args.n_chunks;
   const bool table_in_smem = args.n_chunks <= kSmemChunks;
   const ChunkDesc *chunks = table_in_smem ? s_chunks : args.chunks;
 
-  if (table_in_smem) {
-    const int n16 = args.n_chunks * (int) (sizeof(ChunkDesc) / 16);
-    for (int i = threadIdx.x; i < n16; i += blockDim.x)
-      reinterpret_cast<int4 *>(s_chunks)[i] = reinterpret_cast<const int4 *>(args.chunks)[i];
+  // A CTA of a 4096-board launch lives for ONE pass, so its start-up is part of every pass: the first group's input
+  // codes are requested before anything else (their DRAM latency runs under the barrier set-up), the chunk and exp
+  // tables arrive by one bulk copy instead of per-thread loads, and the first ring fills need no global read.
+  LaneCodes codes_first;
+  {
+    const long board = ((long) blockIdx.x * n_pairs + pair) * kBoardsPerWarp + m;
+    codes_first = load_codes(args.codes, board, my_groups > 0 && board < args.n_boards, half, q);
   }
-  for (int i = threadIdx.x; i < kExpTblSize; i += blockDim.x) exp_tbl[i] = c_exp2_tbl[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], 1);
       done[s] = 0;
     }
+    mbar_init(tbl_bar, 1);
     mbar_fence_init();
     for (int s = 0; s < n_stages && s < total_chunks; ++s) {  // initial fill of the ring
-      const ChunkDesc *d = &args.chunks[s % args.n_chunks];
-      mbar_arrive_expect_tx(&full[s], d->bytes);
-      bulk_g2s(ring + (size_t) s * stage_bytes, args.pack + d->src_off, d->bytes, &full[s]);
+      mbar_arrive_expect_tx(&full[s], args.fill_bytes[s]);
+      bulk_g2s(ring + (size_t) s * stage_bytes, args.pack + args.fill_off[s], args.fill_bytes[s], &full[s]);
     }
+    const uint32_t tb = table_in_smem ? (uint32_t) kBlobBytes : (uint32_t) (kExpTblSize * sizeof(double));
+    mbar_arrive_expect_tx(tbl_bar, tb);
+    if (table_in_smem) bulk_g2s(s_chunks, args.blob, tb, tbl_bar);
+    else bulk_g2s(exp_tbl, args.blob + kBlobChunkBytes, tb, tbl_bar);
   }
   __syncthreads();
 
+  const long long t_start = args.team_lag > 0 ? clock64() : 0;
   double2 *abuf = abuf_all + (size_t) pair * args.a_units * 32;
-  const int m = lane >> 2, q = lane & 3;
   double acc[kMaxNBH][2];
   uint32_t rs = 0, rk = 0;   // ring slot of the current chunk, times the ring wrapped
   long n = 0;                // sequence number of the current chunk within this CTA
@@ -252,24 +286,35 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
     const long board0 = (g * n_pairs + pair) * kBoardsPerWarp;
     const long board = board0 + m;
     const bool valid = board < args.n_boards;
+    const bool first_group = g == (long) blockIdx.x;
     double *save_lane = (args.save != nullptr && valid) ? args.save + board0 * 8 + lane * 2 : nullptr;
 
     CAB_PROF_T(t_load)
     {
       // Network::loadBoard (network.cpp:119-123): input = k * 0.4, bit-identical to Piece::code().
       // The pair splits the 8 input units; the previous group's last reads of abuf ended at its final pair barrier.
-      const int8_t *row = args.codes + (valid ? board : 0) * 64;
+      const LaneCodes lc = first_group ? codes_first : load_codes(args.codes, board, valid, half, q);
 #pragma unroll
       for (int tt = 0; tt < 4; ++tt) {
         const int t = 2 * tt + half;
-        const int c0 = valid ? row[8 * t + 2 * q] : 0, c1 = valid ? row[8 * t + 2 * q + 1] : 0;
+        const uint32_t pk = lc.v[tt >> 1] >> (16 * (tt & 1));
+        const int c0 = (int) (int8_t) (pk & 0xffu), c1 = (int) (int8_t) ((pk >> 8) & 0xffu);
         const double2 x = make_double2((double) c0 * 0.4, (double) c1 * 0.4);
         abuf[t * 32 + lane] = x;
         if (save_lane != nullptr) *reinterpret_cast<double2 *>(save_lane + (size_t) t * args.save_stride) = x;
       }
       pair_barrier(pair);
+      if (first_group) mbar_wait(tbl_bar, 0);   // chunk and exp tables present (requested before the input load)
     }
     CAB_PROF_ACC(0, t_load)
+    // Optional staggered teams (CAB_FWD_LAG; measured neutral for one-pass CTAs: the delayed team's gain equals the delay).
+    if (args.team_lag > 0 && first_group) {
+      const int team = warp >> args.team_shift;
+      if (team > 0) {
+        const long long until = t_start + (long long) team * args.team_lag;
+        while (clock64() < until) {}
+      }
+    }
 
     for (int c = 0; c < args.n_chunks; ++c, ++n) {
       CAB_PROF_T(t_desc)
@@ -286,10 +331,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
       mbar_wait(&full[rs], rk & 1);
       CAB_PROF_ACC(2, t_wait)
       CAB_PROF_T(t_mma)
-      double *save_row = (JIT && j0 == 0 && nbh > 0 && save_lane != nullptr) ? save_lane + (size_t) (d.save_in + d.t0) * args.save_stride : nullptr;
-      dispatch_chunk(nbh, JIT && (d.flags & kActIn), acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
-                     ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount,
-                     exp_tbl, save_row, args.save_stride);
+      dispatch_chunk(nbh, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
+                     ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount);
       __syncwarp();
       CAB_PROF_ACC(3, t_mma)
 
@@ -315,36 +358,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
       if (last) {
         // Layer boundary. (1) a = f(theta) on this warp's own tiles, IN REGISTERS and BEFORE the barrier: the wait for
         // the partner (who may still be reading the layer input that the outputs overwrite in place) is spent on the
-        // exp / reciprocal math, and there is no shared-memory round trip. The 4-case switch gives the rolled loop
-        // static register indices; tiles past nbh hold zeros and f(0) = 0. (2) barrier: input fully read.
+        // exp / reciprocal math, and there is no shared-memory round trip. (2) barrier: input fully read.
         // (3) store the activations in place. (4) barrier: outputs visible to the partner.
         double2 *a_out = abuf + (size_t) (d.a_out + j0) * 32;
-        if (THETA && !JIT && args.save_theta != nullptr && valid)
+        if (THETA && args.save_theta != nullptr && valid)
           dispatch_store_global(nbh, acc, args.save_theta + board0 * 8 + lane * 2 + (size_t) (d.save_off + d.tile0 + j0) * args.save_stride,
                                 args.save_stride);
-        if (!JIT) {
-          for (int g4 = 0; g4 * 4 < nbh; ++g4) {
-            switch (g4) {
-              case 0: act_group<0>(acc, exp_tbl); break;
-              case 1: act_group<1>(acc, exp_tbl); break;
-              case 2: act_group<2>(acc, exp_tbl); break;
-              default: act_group<3>(acc, exp_tbl); break;
-            }
-          }
-        }
+        act_all(nbh, acc, exp_tbl);
         CAB_PROF_T(t_bar1)
         pair_barrier(pair);
         CAB_PROF_ACC(7, t_bar1)
         dispatch_store(nbh, acc, a_out, lane);
         const bool owns_tile0 = j0 == 0 && nbh > 0;
-        if (JIT && (d.flags & kFinal) && owns_tile0) {   // JIT: raw pre-activations stay in the buffer; only the output is activated here
-          double2 v = a_out[lane];
-          v.x = act_f_tbl(v.x, exp_tbl);
-          v.y = act_f_tbl(v.y, exp_tbl);
-          a_out[lane] = v;
-          if (save_lane != nullptr) *reinterpret_cast<double2 *>(save_lane + (size_t) d.save_off * args.save_stride) = v;
-        }
-        if (!JIT && save_lane != nullptr)                // K2: keep every layer's activations for the backward pass
+        if (save_lane != nullptr)                        // K2: keep every layer's activations for the backward pass
           for (int j = 0; j < nbh; ++j)
             *reinterpret_cast<double2 *>(save_lane + (size_t) (d.save_off + d.tile0 + j0 + j) * args.save_stride) = a_out[j * 32 + lane];
         if ((d.flags & kFinal) && owns_tile0 && args.out != nullptr && valid && q == 0) args.out[board] = a_out[lane].x;

@@ -245,9 +245,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
         for (int j = 0; j < kMaxNBH; ++j) acc[j][0] = acc[j][1] = 0.0;
       }
       mbar_wait(&full[rs], rk & 1);
-      dispatch_chunk(nbh, false, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
-                     ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount,
-                     nullptr, nullptr, 0);
+      dispatch_chunk(nbh, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
+                     ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount);
       __syncwarp();
       if (lane == 0) {
         const uint32_t old = atomicAdd(&done[rs], 1u);
