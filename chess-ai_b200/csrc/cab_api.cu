@@ -203,6 +203,19 @@ static void build_plan(const cab_net *net, bool transposed, StreamPlan *plan) {
     ping = 1 - ping;
   }
   plan->total_doubles = off;
+  // Forward stream: a final one-output layer (dims normalisation always appends 1) that fits one chunk, behind a layer
+  // of a single n-block, is fused into that layer's epilogue as a dot product (mlp_stream_kernel.cuh: kDot).
+  static const bool fuse = getenv("CAB_FWD_FUSE_OUT") ? atoi(getenv("CAB_FWD_FUSE_OUT")) != 0 : true;
+  if (fuse && !transposed && L >= 3 && net->dims[L - 1] == 1 && plan->chunks.size() >= 2) {
+    ChunkDesc &out_chunk = plan->chunks.back();
+    ChunkDesc &prev_last = plan->chunks[plan->chunks.size() - 2];
+    const int prev_tiles = ceil_div(net->dims[L - 2], 8);
+    const bool one_chunk = (out_chunk.flags & kFirst) && (out_chunk.flags & kLast) && out_chunk.nb == 1 && out_chunk.tcount == prev_tiles;
+    if (one_chunk && prev_tiles <= kMaxNB && prev_last.layer + 1 == out_chunk.layer && (prev_last.flags & kLast) && prev_last.nb == prev_tiles) {
+      out_chunk.flags |= kDot;
+      prev_last.flags |= kPreDot;
+    }
+  }
 }
 
 static int upload_plan(StreamPlan *plan) {
@@ -213,6 +226,8 @@ static int upload_plan(StreamPlan *plan) {
     std::vector<uint8_t> blob(kBlobBytes, 0);
     memcpy(blob.data(), plan->chunks.data(), std::min(plan->chunks.size(), (size_t) kSmemChunks) * sizeof(ChunkDesc));
     CAB_CUDA(cudaMemcpyFromSymbol(blob.data() + kBlobChunkBytes, c_exp2_tbl, kExpTblSize * sizeof(double)));
+    double *tbl8 = reinterpret_cast<double *>(blob.data() + kBlobChunkBytes);
+    for (int j = 0; j < kExpTblSize; ++j) tbl8[j] *= 0.125;     // act_f_tbl wants T[j] / 8 (exact scaling)
     CAB_CUDA(cudaMalloc(&plan->d_blob, kBlobBytes));
     CAB_CUDA(cudaMemcpy(plan->d_blob, blob.data(), kBlobBytes, cudaMemcpyHostToDevice));
   }
@@ -349,7 +364,8 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
     net->launches++;
     return CAB_OK;
   }
-  if (d_theta != nullptr) mlp_forward_kernel<false, true><<<grid, n_cons * 64, smem, stream>>>(a);
+  if (d_theta != nullptr) mlp_forward_kernel<false, true, true><<<grid, n_cons * 64, smem, stream>>>(a);
+  else if (d_save != nullptr) mlp_forward_kernel<false, true><<<grid, n_cons * 64, smem, stream>>>(a);
   else mlp_forward_kernel<false><<<grid, n_cons * 64, smem, stream>>>(a);
   net->launches++;
   CAB_CUDA(cudaGetLastError());
@@ -414,6 +430,7 @@ static int init_net(cab_net *net, const std::vector<int> &dims, int device) {
   net->fp64_ok = consumer_warps_for(std::max(net->fwd.a_units, net->bwd.a_units), net->stage_bytes) > 0;
   CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   return CAB_OK;
 }

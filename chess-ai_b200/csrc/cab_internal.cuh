@@ -30,7 +30,9 @@ constexpr int kMaxNB = 32;                              // output tiles of one n
 constexpr int kMaxNBH = 16;                             // output tiles one warp accumulates in registers
 constexpr int kUnitBytes = 512;                         // 32 lanes x double2
 
-enum ChunkFlags : uint8_t { kFirst = 1, kLast = 2, kFinal = 4, kActIn = 8 };  // kActIn: apply f() to the A operand on load
+// kDot: the chunk is a one-output layer evaluated as a dot product on the previous layer's activations still in
+// registers (forward kernel); kPreDot: last chunk of the layer in front of it (its activations are not stored)
+enum ChunkFlags : uint8_t { kFirst = 1, kLast = 2, kFinal = 4, kDot = 8, kPreDot = 16 };
 
 struct __align__(16) ChunkDesc {
   uint32_t src_off;  // byte offset into the packed stream
@@ -316,19 +318,23 @@ constexpr int kExpTblSize = 256;
 //     the product exact inside it
 //   * 8 / (1 + exp(t)) = 1 / d8 by MUFU.RCP64H (relative error 9.3e-7) and ONE cubic step y (1 + e + e^2), e = 1 - d8 y
 //     (residual e^3 < 1e-18);  f = 8 / (1 + exp(t)) - 4
-// 13 fp64-pipe operations (round 1: 16; the libm expression: ~51 lane-clocks). `tbl` is the shared-memory copy of c_exp2_tbl.
+// 13 fp64-pipe operations (round 1: 16; the libm expression: ~51 lane-clocks). An fp64 operation holds the issue port
+// for two cycles and the integer / MUFU / LDS instructions do not hide under it (tools/act_bench.cu: 40 issue cycles per
+// warp activation against a 26-cycle pipe floor), so those are kept few too.
+// `tbl` is the shared-memory table T[j] / 8 = 2^(j/256 - 3), j = 0..255 (c_exp2_tbl scaled exactly).
 __device__ __forceinline__ double act_f_tbl(double x, const double *tbl) {
   const int hx = __double2hiint(x);
   const bool big = (unsigned) (hx & 0x7fffffff) >= 0x405e0000u;           // |x| >= 120.0 (0x405E000000000000), inf, NaN
-  const double xc = __hiloint2double(big ? ((hx & (int) 0x80000000) | 0x405e0000) : hx, big ? 0 : __double2loint(x));
+  // (the low word stays: +-[120, 120 + 2^-14) saturates exactly like +-120)
+  const double xc = __hiloint2double(big ? ((hx & (int) 0x80000000) | 0x405e0000) : hx, __double2loint(x));
   const double magic = 6755399441055744.0;
   const double nm = fma(xc, -184.66496523378732, magic);   // n = rint(-x/2 * 256/ln2)
   const double nd = nm - magic;
   double r = fma(nd, 0.00541521234663378, xc);              // r' = x + n * ln2_hi/128   (fdlibm's split of ln 2, scaled exactly)
   r = fma(nd, 1.4907929134926466e-12, r);                   //        + n * ln2_lo/128
   const int ki = __double2loint(nm);
-  const double tj = tbl[ki & 255];
-  const double t8 = __hiloint2double(__double2hiint(tj) + (((ki >> 8) - 3) << 20), __double2loint(tj));
+  const double tj = tbl[ki & 255];                          // T[j] / 8
+  const double t8 = __hiloint2double(__double2hiint(tj) + ((ki & (int) 0xffffff00) << 12), __double2loint(tj));   // * 2^k
   double q = fma(r, 2.6041666666666665e-03, -2.0833333333333332e-02);   // 1/384, -1/48
   q = fma(r, q, 0.125);
   q = fma(r, q, -0.5);

@@ -148,6 +148,30 @@ __device__ __forceinline__ void dispatch_store_global(int nbh, const double (&ac
 }
 #undef CAB_NB_CASE
 
+// sum_j acc[j] . w[j] for this warp's NBH tiles; w_addr = this lane's 16 bytes of the first tile's unit
+template <int NBH>
+__device__ __forceinline__ double dot_acc(const double (&acc)[kMaxNBH][2], uint32_t w_addr) {
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int j = 0; j < NBH; ++j) {
+    const double2 w = lds_frag(w_addr + j * kUnitBytes);
+    s0 = fma(acc[j][0], w.x, s0);
+    s1 = fma(acc[j][1], w.y, s1);
+  }
+  return s0 + s1;
+}
+#define CAB_NB_CASE(N) \
+  case N: return dot_acc<N>(acc, w_addr);
+__device__ __forceinline__ double dispatch_dot(int nbh, const double (&acc)[kMaxNBH][2], uint32_t w_addr) {
+  switch (nbh) {
+    CAB_NB_CASE(1) CAB_NB_CASE(2) CAB_NB_CASE(3) CAB_NB_CASE(4) CAB_NB_CASE(5) CAB_NB_CASE(6) CAB_NB_CASE(7)
+    CAB_NB_CASE(8) CAB_NB_CASE(9) CAB_NB_CASE(10) CAB_NB_CASE(11) CAB_NB_CASE(12) CAB_NB_CASE(13) CAB_NB_CASE(14)
+    CAB_NB_CASE(15) CAB_NB_CASE(16)
+    default: return 0.0;
+  }
+}
+#undef CAB_NB_CASE
+
 #define CAB_NB_CASE(N) \
   case N: store_acc<N>(acc, a_out, lane); break;
 __device__ __forceinline__ void dispatch_store(int nbh, const double (&acc)[kMaxNBH][2], double2 *a_out, int lane) {
@@ -200,8 +224,9 @@ struct ForwardArgs {
 __host__ __device__ inline size_t fwd_smem_ring(int n_stages, int stage_bytes) { return (size_t) n_stages * stage_bytes; }
 __host__ __device__ inline size_t fwd_smem_abuf(int n_pairs, int a_units) { return (size_t) n_pairs * a_units * kUnitBytes; }
 constexpr size_t kBlobChunkBytes = (size_t) kSmemChunks * sizeof(ChunkDesc), kBlobBytes = kBlobChunkBytes + kExpTblSize * sizeof(double);
+constexpr size_t kDotScratchBytes = (size_t) (kConsumerWarps / 2) * kBoardsPerWarp * sizeof(double);   // pair exchange of the fused output layer
 __host__ __device__ inline size_t fwd_smem_tail(int n_stages) {
-  return kBlobBytes + (size_t) (n_stages + 1) * sizeof(uint64_t) + (size_t) n_stages * sizeof(uint32_t) + 16;
+  return kBlobBytes + kDotScratchBytes + (size_t) (n_stages + 1) * sizeof(uint64_t) + (size_t) n_stages * sizeof(uint32_t) + 16;
 }
 
 #define CAB_PROF_T(var) long long var = 0; if (PROF) var = clock64();
@@ -223,8 +248,10 @@ __device__ __forceinline__ LaneCodes load_codes(const int8_t *codes, long board,
   return c;
 }
 
-// THETA = true: also writes every layer's pre-activations to args.save_theta (K2 as the reference's API returns it).
-template <bool PROF, bool THETA = false>
+// SAVE = true: K2, every layer's activations also go to args.save (propagate_for_training, network.cpp:139-153).
+// THETA = true (with SAVE): the pre-activations too, to args.save_theta (K2 as the reference's API returns it).
+// The plain evaluator (SAVE = false) carries none of that code or its registers.
+template <bool PROF, bool SAVE = false, bool THETA = false>
 __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const ForwardArgs args) {
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CAB_PROF_T(t_kernel)
@@ -235,7 +262,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
   double2 *abuf_all = reinterpret_cast<double2 *>(smem + fwd_smem_ring(n_stages, stage_bytes));
   ChunkDesc *s_chunks = reinterpret_cast<ChunkDesc *>(smem + fwd_smem_ring(n_stages, stage_bytes) + fwd_smem_abuf(n_pairs, args.a_units));
   double *exp_tbl = reinterpret_cast<double *>(s_chunks + kSmemChunks);  // 2^(j/256) for the table-driven exp
-  uint64_t *full = reinterpret_cast<uint64_t *>(exp_tbl + kExpTblSize);
+  double *dot_scratch = exp_tbl + kExpTblSize;                           // [pair][8]: half 1's partial sums of the fused output layer
+  uint64_t *full = reinterpret_cast<uint64_t *>(dot_scratch + kDotScratchBytes / sizeof(double));
   uint64_t *tbl_bar = full + n_stages;                                   // completes when the tables have landed
   uint32_t *done = reinterpret_cast<uint32_t *>(tbl_bar + 1);            // arrivals per ring slot, monotonically increasing
 
@@ -243,8 +271,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
   const int pair = warp >> 1, half = pair_half(warp);
   const int m = lane >> 2, q = lane & 3;
   // chunks this CTA will consume, in order: (groups it owns) x n_chunks
-  const long my_groups = args.n_groups > blockIdx.x ? (args.n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const long total_chunks = my_groups * args.n_chunks;
+  const int my_groups = args.n_groups > blockIdx.x ? (int) ((args.n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int total_chunks = my_groups * args.n_chunks;   // (a CTA never sees 2^31 chunks: 2^20 groups of <= 2^11 chunks)
   const bool table_in_smem = args.n_chunks <= kSmemChunks;
   const ChunkDesc *chunks = table_in_smem ? s_chunks : args.chunks;
 
@@ -278,7 +306,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
   double2 *abuf = abuf_all + (size_t) pair * args.a_units * 32;
   double acc[kMaxNBH][2];
   uint32_t rs = 0, rk = 0;   // ring slot of the current chunk, times the ring wrapped
-  long n = 0;                // sequence number of the current chunk within this CTA
+  int n = 0;                 // sequence number of the current chunk within this CTA
   const uint32_t abuf_addr = smem_u32(abuf) + (uint32_t) lane * 16u;
   const uint32_t ring_addr = smem_u32(ring) + (uint32_t) lane * 16u;
 
@@ -287,7 +315,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
     const long board = board0 + m;
     const bool valid = board < args.n_boards;
     const bool first_group = g == (long) blockIdx.x;
-    double *save_lane = (args.save != nullptr && valid) ? args.save + board0 * 8 + lane * 2 : nullptr;
+    // K2: this lane's 16 bytes inside unit row 0 of the saved-activation tensor (unit layout [unit][board][8])
+    double *save_lane = (SAVE && args.save != nullptr && valid) ? args.save + board0 * 8 + lane * 2 : nullptr;
 
     CAB_PROF_T(t_load)
     {
@@ -301,7 +330,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
         const int c0 = (int) (int8_t) (pk & 0xffu), c1 = (int) (int8_t) ((pk >> 8) & 0xffu);
         const double2 x = make_double2((double) c0 * 0.4, (double) c1 * 0.4);
         abuf[t * 32 + lane] = x;
-        if (save_lane != nullptr) *reinterpret_cast<double2 *>(save_lane + (size_t) t * args.save_stride) = x;
+        if (SAVE && save_lane != nullptr) *reinterpret_cast<double2 *>(save_lane + (size_t) t * args.save_stride) = x;
       }
       pair_barrier(pair);
       if (first_group) mbar_wait(tbl_bar, 0);   // chunk and exp tables present (requested before the input load)
@@ -319,9 +348,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
     for (int c = 0; c < args.n_chunks; ++c, ++n) {
       CAB_PROF_T(t_desc)
       const ChunkDesc d = chunks[c];
-      const bool first = d.flags & kFirst, last = d.flags & kLast;
+      const bool dot = d.flags & kDot;
+      const bool first = (d.flags & kFirst) && !dot, last = (d.flags & kLast) && !dot;
       int j0, nbh;
-      split_tiles(d.nb, d.layer, half, j0, nbh);
+      // a fused output layer works on the PREVIOUS layer's tiles (its input units), split like that layer was
+      split_tiles(dot ? d.tcount : d.nb, dot ? d.layer - 1 : d.layer, half, j0, nbh);
       if (first) {
 #pragma unroll
         for (int j = 0; j < kMaxNBH; ++j) acc[j][0] = acc[j][1] = 0.0;
@@ -331,8 +362,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
       mbar_wait(&full[rs], rk & 1);
       CAB_PROF_ACC(2, t_wait)
       CAB_PROF_T(t_mma)
-      dispatch_chunk(nbh, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
-                     ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount);
+      double dot_sum = 0.0;
+      if (!dot) {
+        dispatch_chunk(nbh, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
+                       ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount);
+      } else {
+        // One-output layer (network.cpp:99-114 with N = 1) on the activations this warp still holds in registers:
+        // lane (m, q) owns features 8 (j0 + j) + 2q + {0, 1} of board m; the chunk's unit t keeps W[8t + 2q' + h][0]
+        // in lane q' (B fragment of output column 0), so all lanes of one q read the same 16 bytes.
+        dot_sum = dispatch_dot(nbh, acc, smem_u32(ring) + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes + (uint32_t) q * 16u);
+        dot_sum += __shfl_xor_sync(0xffffffffu, dot_sum, 1);
+        dot_sum += __shfl_xor_sync(0xffffffffu, dot_sum, 2);
+      }
       __syncwarp();
       CAB_PROF_ACC(3, t_mma)
 
@@ -342,7 +383,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
       if (lane == 0) {
         const uint32_t old = atomicAdd(&done[rs], 1u);
         if ((old + 1) % (uint32_t) n_warps == 0) {
-          const long refill = n + n_stages;
+          const int refill = n + n_stages;
           if (refill < total_chunks) {
             const ChunkDesc *nd = &chunks[refill % args.n_chunks];
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -355,28 +396,46 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_forward_kernel(const Forwa
       CAB_PROF_ACC(4, t_refill)
 
       CAB_PROF_T(t_act)
-      if (last) {
+      if (dot) {
+        // the pair's two partial sums meet in shared memory; half 0 finishes the board: theta, y = f(theta), outputs
+        double *scratch = dot_scratch + pair * kBoardsPerWarp;
+        if (half == 1 && q == 0) scratch[m] = dot_sum;
+        pair_barrier(pair);
+        if (half == 0) {
+          const double theta = dot_sum + scratch[m];
+          const double y = act_f_tbl(theta, exp_tbl);
+          const size_t goff = (size_t) board0 * 8 + lane * 2 + (size_t) d.save_off * args.save_stride;
+          if (THETA && args.save_theta != nullptr && valid)
+            *reinterpret_cast<double2 *>(args.save_theta + goff) = make_double2(q == 0 ? theta : 0.0, 0.0);
+          if (SAVE && args.save != nullptr && valid) *reinterpret_cast<double2 *>(args.save + goff) = make_double2(q == 0 ? y : 0.0, 0.0);
+          if (args.out != nullptr && valid && q == 0) args.out[board] = y;
+        }
+      } else if (last) {
         // Layer boundary. (1) a = f(theta) on this warp's own tiles, IN REGISTERS and BEFORE the barrier: the wait for
         // the partner (who may still be reading the layer input that the outputs overwrite in place) is spent on the
         // exp / reciprocal math, and there is no shared-memory round trip. (2) barrier: input fully read.
         // (3) store the activations in place. (4) barrier: outputs visible to the partner.
+        // In front of a fused output layer (kPreDot) the activations simply stay in registers: no barrier, no store;
+        // K2 / theta export write them to global memory straight from the registers.
+        const bool keep = d.flags & kPreDot;
         double2 *a_out = abuf + (size_t) (d.a_out + j0) * 32;
         if (THETA && args.save_theta != nullptr && valid)
           dispatch_store_global(nbh, acc, args.save_theta + board0 * 8 + lane * 2 + (size_t) (d.save_off + d.tile0 + j0) * args.save_stride,
                                 args.save_stride);
         act_all(nbh, acc, exp_tbl);
-        CAB_PROF_T(t_bar1)
-        pair_barrier(pair);
-        CAB_PROF_ACC(7, t_bar1)
-        dispatch_store(nbh, acc, a_out, lane);
-        const bool owns_tile0 = j0 == 0 && nbh > 0;
-        if (save_lane != nullptr)                        // K2: keep every layer's activations for the backward pass
-          for (int j = 0; j < nbh; ++j)
-            *reinterpret_cast<double2 *>(save_lane + (size_t) (d.save_off + d.tile0 + j0 + j) * args.save_stride) = a_out[j * 32 + lane];
-        if ((d.flags & kFinal) && owns_tile0 && args.out != nullptr && valid && q == 0) args.out[board] = a_out[lane].x;
-        CAB_PROF_T(t_bar2)
-        pair_barrier(pair);
-        CAB_PROF_ACC(7, t_bar2)
+        if (SAVE && save_lane != nullptr)                // K2: keep every layer's activations for the backward pass
+          dispatch_store_global(nbh, acc, save_lane + (size_t) (d.save_off + d.tile0 + j0) * args.save_stride, args.save_stride);
+        if (!keep) {
+          CAB_PROF_T(t_bar1)
+          pair_barrier(pair);
+          CAB_PROF_ACC(7, t_bar1)
+          dispatch_store(nbh, acc, a_out, lane);
+          const bool owns_tile0 = j0 == 0 && nbh > 0;
+          if ((d.flags & kFinal) && owns_tile0 && args.out != nullptr && valid && q == 0) args.out[board] = a_out[lane].x;
+          CAB_PROF_T(t_bar2)
+          pair_barrier(pair);
+          CAB_PROF_ACC(7, t_bar2)
+        }
       }
       CAB_PROF_ACC(5, t_act)
     }

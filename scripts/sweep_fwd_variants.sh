@@ -3,9 +3,6 @@
 #   scripts/sweep_fwd_variants.sh > gpurun_out/fwd_sweep.jsonl
 B=chess-ai_b200/lib/fwd_bench
 W=tests/golden/latest_weights.f64
-run() { env "$@" $B $W 1048576 4096 4 6; }
-run CAB_X=0
-run CAB_X=0
-run CAB_FWD_PAIRS=7
-run CAB_FWD_PAIRS=6
-run CAB_FWD_TEAM_SHIFT=3 CAB_FWD_LAG=4000
+run() { env "$@" $B $W 1048576 4096 ${STREAMS:-4} 6; }
+run CAB_FWD_FUSE_OUT=1
+run CAB_FWD_FUSE_OUT=0
