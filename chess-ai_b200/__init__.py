@@ -93,6 +93,14 @@ _SIGS = {
     "cab_train_batch_bf16_host": [_vp, _i8p, _f64p, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp],
     "cab_train_batch_bf16_dev": [_vp, _vp, _vp, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp, _vp],
     "cab_grad_bf16_dev": [_vp, _vp, _vp, C.c_long, _vp],
+    "cab_mcts_create": [_vp, _vp, C.POINTER(_vp)],
+    "cab_mcts_destroy": [_vp],
+    "cab_mcts_set_positions": [_vp, _i8p, _i8p, _vp],
+    "cab_mcts_run": [_vp, C.c_int, C.c_long, _vp],
+    "cab_mcts_root_children": [_vp, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f64p, _i32p, _f64p, _ip, _ip, _dp],
+    "cab_mcts_game_state": [_vp, C.c_int, _i8p, _ip, _ip, _ip, _ip],
+    "cab_mcts_cases": [_vp, _vp, _vp, C.c_long, _lp],
+    "cab_movegen_host": [C.c_int, _i8p, _i8p, C.c_int, C.c_int, C.c_int, _i32p, _u8p, _vp],
     "cab_measure_pipe_peak": [C.c_int, C.c_int, _dp],
     "cab_net_launch_count": [_vp, _lp],
 }
@@ -496,3 +504,83 @@ class NetworkStorage:
     def saveBoard(cls, board, value):
         if cls._network_training_case is not None:
             cls._network_training_case(Board(board.records.copy()), value)
+
+
+# ---- MCTS self-play resident on the GPU (csrc/cab_mcts.cu) ---------------------------------------------------------
+class MctsParams(C.Structure):
+    _fields_ = [("games", C.c_int), ("roots", C.c_int), ("playouts_per_move", C.c_int), ("in_flight", C.c_int), ("max_moves", C.c_int),
+                ("network_priors", C.c_int), ("noise", C.c_int), ("reserved", C.c_int), ("save_ratio", C.c_double), ("seed", C.c_uint64)]
+
+
+class MctsStats(C.Structure):
+    _fields_ = [(n, C.c_long) for n in ("playouts", "expansions", "boards_evaluated", "moves_played", "games_finished", "searches_done",
+                                        "rounds", "arena_full", "eval_full", "cases_kept")] + [("seconds", C.c_double), ("evaluator_seconds", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class SelfPlay:
+    """tree::MCTS self-play with virtual-loss leaf batching, trees and rules on the device (tree.cpp, decider.cpp:31-61)."""
+
+    def __init__(self, net, games, playouts_per_move, roots=1, in_flight=8, max_moves=40, network_priors=0, noise=0, save_ratio=0.0, seed=1234):
+        self.net = net
+        self.params = MctsParams(games, roots, playouts_per_move, in_flight, max_moves, network_priors, noise, 0, save_ratio, seed)
+        self._h = _vp(None)
+        _ck(lib().cab_mcts_create(net._h, C.byref(self.params), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().cab_mcts_destroy(self._h)
+            self._h = _vp(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_positions(self, codes, side, no_capture=None):
+        codes = np.ascontiguousarray(codes, dtype=np.int8).reshape(self.params.games, 64)
+        side = np.ascontiguousarray(side, dtype=np.int8)
+        nc = None if no_capture is None else np.ascontiguousarray(no_capture, dtype=np.int32)
+        _ck(lib().cab_mcts_set_positions(self._h, codes, side, None if nc is None else nc.ctypes.data))
+
+    def run(self, search_only=False, max_rounds=0):
+        st = MctsStats()
+        _ck(lib().cab_mcts_run(self._h, 1 if search_only else 0, max_rounds, C.byref(st)))
+        return st.as_dict()
+
+    def root_children(self, game, root=-1, cap=256):
+        fr, to, vi = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        pr, vs = np.zeros(cap), np.zeros(cap)
+        n, rv, rvs = C.c_int(0), C.c_int(0), C.c_double(0)
+        _ck(lib().cab_mcts_root_children(self._h, game, root, cap, fr, to, pr, vi, vs, C.byref(n), C.byref(rv), C.byref(rvs)))
+        k = min(n.value, cap)
+        return {"from": fr[:k], "to": to[:k], "prior": pr[:k], "visits": vi[:k], "value_sum": vs[:k], "root_visits": rv.value,
+                "root_value_sum": rvs.value}
+
+    def game_state(self, game):
+        codes = np.zeros(64, np.int8)
+        side, over, result, moves = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        _ck(lib().cab_mcts_game_state(self._h, game, codes, C.byref(side), C.byref(over), C.byref(result), C.byref(moves)))
+        return {"codes": codes, "side": side.value, "over": over.value, "result": result.value, "moves_played": moves.value}
+
+    def cases(self):
+        n = C.c_long(0)
+        _ck(lib().cab_mcts_cases(self._h, None, None, 0, C.byref(n)))
+        codes, targets = np.zeros((max(n.value, 1), 64), np.int8), np.zeros(max(n.value, 1))
+        _ck(lib().cab_mcts_cases(self._h, codes.ctypes.data, targets.ctypes.data, n.value, C.byref(n)))
+        return codes[:n.value], targets[:n.value]
+
+
+def device_movegen(codes, side, queen_only=False, cap=256, no_reply=False, device=0):
+    """Legal moves of n positions by the kernels' own rules (csrc/chess_rules.cuh), reference order."""
+    codes = np.ascontiguousarray(codes, dtype=np.int8).reshape(-1, 64)
+    side = np.ascontiguousarray(side, dtype=np.int8)
+    n = len(codes)
+    counts, moves = np.zeros(n, np.int32), np.zeros((n, cap, 3), np.uint8)
+    flags = np.zeros((n, cap), np.uint8) if no_reply else None
+    _ck(lib().cab_movegen_host(device, codes, side, n, 1 if queen_only else 0, cap, counts, moves.reshape(-1),
+                               None if flags is None else flags.ctypes.data))
+    return (counts, moves, flags) if no_reply else (counts, moves)

@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libchessai_b200.so")
-SOURCES = ["cab_api.cu", "cab_train.cu", "cab_tc.cu", "cab_leafq.cu", "cab_prediction.cu"]
-HEADERS = ["cab_internal.cuh", "mlp_stream_kernel.cuh", "tc_gemm_bf16.cuh", "mlp_tc_fused.cuh", "train_kernels.cuh", os.path.join("..", "..", "include", "chessai_b200.h"),
+SOURCES = ["cab_api.cu", "cab_train.cu", "cab_tc.cu", "cab_leafq.cu", "cab_prediction.cu", "cab_mcts.cu"]
+HEADERS = ["cab_internal.cuh", "chess_rules.cuh", "mlp_stream_kernel.cuh", "tc_gemm_bf16.cuh", "mlp_tc_fused.cuh", "train_kernels.cuh", os.path.join("..", "..", "include", "chessai_b200.h"),
            os.path.join("..", "host", "fastchess.hpp")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -48,7 +48,8 @@ def build(verbose=False, force=False):
     host = os.path.join(HERE, "host")
     gxx = os.environ.get("CXX", "g++")
     fc = os.path.join(LIB_DIR, "libfastchess.so")
-    fc_deps = [os.path.join(host, "fastchess_c.cpp"), os.path.join(host, "fastchess.hpp"), os.path.join(host, "cases.hpp")]
+    fc_deps = [os.path.join(host, "fastchess_c.cpp"), os.path.join(host, "fastchess.hpp"), os.path.join(host, "cases.hpp"),
+               os.path.join(CSRC, "chess_rules.cuh")]
     if force or _stale(fc, fc_deps):
         subprocess.check_call([gxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-static-libstdc++",
                                "-static-libgcc", "-o", fc, fc_deps[0]])

@@ -1,6 +1,7 @@
 // fastchess_c.cpp — plain-C entry points over fastchess.hpp for the Python tests (ctypes). Host-side only.
 #include "cases.hpp"
 #include "fastchess.hpp"
+#include "../csrc/chess_rules.cuh"   // the device rules, compiled for the host: pinned on the CPU by tests/test_chess_rules.py
 
 using namespace fastchess;
 
@@ -59,5 +60,19 @@ FC_API long fc_shard_read(const char *path, int8_t *codes_out, double *targets_o
   if (!cases::read_shard(path, cs)) return -1;
   for (long i = 0; i < (long) cs.size() && i < cap; ++i) { std::memcpy(codes_out + i * 64, cs[(size_t) i].codes, 64); targets_out[i] = cs[(size_t) i].target; }
   return (long) cs.size();
+}
+}
+
+// ---- csrc/chess_rules.cuh (what the MCTS kernels run) through the same kind of entry points ----
+extern "C" {
+FC_API int cr_moves(const int8_t *codes, int side, uint8_t *moves_out, int queen_only) {
+  return crules::generate_moves(codes, side, moves_out, queen_only != 0);
+}
+FC_API int cr_apply(int8_t *codes, int from, int to, int promo) { return crules::apply_move(codes, from, to, promo) ? 1 : 0; }
+FC_API int cr_has_move(const int8_t *codes, int side) { return crules::has_legal_move(codes, side) ? 1 : 0; }
+FC_API int cr_material(const int8_t *codes, int color) { return crules::material(codes, color); }
+FC_API int cr_in_check(const int8_t *codes, int side) {
+  const int ks = crules::king_square(codes, side);
+  return ks >= 0 && crules::attacked(crules::plain(codes), ks >> 3, ks & 7, side) ? 1 : 0;
 }
 }

@@ -133,6 +133,53 @@ CAB_API int cab_prediction_host(cab_net *net, const int8_t *codes64, int side_to
 CAB_API int cab_prior_softmax_host(int device, const double *logits, const int *seg_off, int n_seg, const double *color_mult,
                                    double *priors_out);
 
+/* ---- MCTS self-play resident on the GPU (new; tree::MCTS + Decider::prediction + Game::tryMove as kernels) ----------- */
+/* BASELINE.json configs[2]. The trees (one per game and root), the playouts, the node expansion — legal moves in the
+ * reference's order (chess/game.cpp:228-263), child boards written straight into the evaluator's input buffer, the
+ * "opponent has no reply" test (mcts_network/decider.cpp:47-57) — the priors (tree.cpp:299-306), the virtual losses, the
+ * move choice (tree.cpp:122-142,195) and the game rules (game.cpp:847-890) all run on the device; per round the host
+ * launches three kernels and reads one counter. Search semantics are tree.cpp's: with in_flight = 1, roots = 1 and
+ * noise = 0 a search equals tree::MCTS::mcts() (visit counts exactly; tests/test_mcts_gpu.py). */
+typedef struct cab_mcts cab_mcts;
+typedef struct cab_mcts_params {
+  int games;              /* concurrent games on this device */
+  int roots;              /* independent trees per move, merged like Node::combineNodes (DEFAULT_NUM_THREADS, tree.cpp:147) */
+  int playouts_per_move;  /* split over the roots (NUM_SIMULATIONS_PER_THREAD = playouts_per_move / roots) */
+  int in_flight;          /* playouts in flight per tree under virtual loss; 1 = the reference's sequential search */
+  int max_moves;          /* a game stops after this many moves (or at mate / stalemate / 50 plies without capture) */
+  int network_priors;     /* 0: decider.cpp:52-57 as shipped (constant logit 20 unless the opponent has no reply); 1: every child evaluated */
+  int noise;              /* 1: Dirichlet(0.2) noise mixed 25 % into the root priors (tree.cpp:318-347), Philox-driven */
+  int reserved;
+  double save_ratio;      /* probability of keeping the board after a move as a training case (initialization.cpp:221-227) */
+  uint64_t seed;
+} cab_mcts_params;
+typedef struct cab_mcts_stats {
+  long playouts, expansions, boards_evaluated, moves_played, games_finished, searches_done, rounds;
+  long arena_full, eval_full, cases_kept;
+  double seconds;            /* wall time inside cab_mcts_run */
+  double evaluator_seconds;  /* of which the network evaluator was running (CUDA events around its launches) */
+} cab_mcts_stats;
+CAB_API int cab_mcts_create(cab_net *net, const cab_mcts_params *params, cab_mcts **out);
+CAB_API int cab_mcts_destroy(cab_mcts *q);
+/* start positions (default: the start position): codes [games][64], side [games] (+1 white / -1 black to move),
+ * no_capture [games] or null. Restarts every game. */
+CAB_API int cab_mcts_set_positions(cab_mcts *q, const int8_t *codes, const int8_t *side, const int *no_capture);
+/* search_only = 0: play every game to its end; 1: search the current move of every game and stop (nothing is played).
+ * max_rounds > 0 bounds the call (call again to continue). */
+CAB_API int cab_mcts_run(cab_mcts *q, int search_only, long max_rounds, cab_mcts_stats *stats);
+/* searched root of one game: children in std::map<Move> order with from / to square, prior, visit count, value sum;
+ * root = -1 merges the roots (Node::combineNodes), root >= 0 reads one tree. */
+CAB_API int cab_mcts_root_children(cab_mcts *q, int game, int root, int cap, int *from, int *to, double *prior, int *visits,
+                                   double *value_sum, int *n_children, int *root_visits, double *root_value_sum);
+CAB_API int cab_mcts_game_state(cab_mcts *q, int game, int8_t *codes64, int *side, int *over, int *result, int *moves_played);
+/* training cases of the finished games: target = 10 * (4 * clamp(2v - 1) + result) / 5 (make_cases.cpp:36-42) */
+CAB_API int cab_mcts_cases(cab_mcts *q, int8_t *codes_out, double *targets_out, long cap, long *n);
+/* the kernels' own move generator on n positions (parity tests against the recorded reference games):
+ * moves_out [n][cap][3] = (from, to, promo), reference order (game.cpp:228-263, promotions Q R N B unless queen_only);
+ * no_reply_out (optional, needs queen_only) [n][cap]: 1 where the move leaves the opponent no legal move */
+CAB_API int cab_movegen_host(int device, const int8_t *codes, const int8_t *side, int n, int queen_only, int cap,
+                             int *n_moves_out, uint8_t *moves_out, uint8_t *no_reply_out);
+
 /* ---- bf16 tensor-core forward (tcgen05 + TMEM + TMA) for WIDE networks ------------------------------------------ */
 /* Same forward (network.cpp:92-117) with bf16 operands, fp32 accumulation in tensor memory and f() in fp32. Only for
  * networks whose hidden widths are multiples of 256 (e.g. Network({2048,2048,2048,2048})); CAB_EINVAL otherwise.

@@ -28,6 +28,7 @@
 
 #include "mcts_network/network.h"
 #include "mcts_network/decider.h"
+#include "mcts_network/tree.h"
 #include "chess/game.h"
 #include "chess/piece.h"
 #include "main/network/make_cases.h"
@@ -417,4 +418,105 @@ extern "C" int ref_prediction_codes(void *net, const int8_t *codes, int white_to
   }
   delete g;
   return k;
+}
+
+// ---- tree::MCTS on a position given as codes (golden data for the GPU-resident search, cab_mcts.cu) ---------------
+// The reference's own sequential search: root = new Node(colour); expand_node(root) (NO Dirichlet noise — the noise is
+// added by run_mcts_multithreaded, tree.cpp:182-183, from an un-vendored GSL); MCTS::mcts() with `sims` playouts of
+// SIMULATION_SEARCH_DEPTH plies (tree.cpp:202-262). Per root child, in std::map<Move> order: from / to square, prior,
+// visit count, value sum; the root's own visit count and value sum. Returns the number of children.
+extern "C" int ref_mcts_root(void *net, const int8_t *codes, int white_to_move, int no_capture, int sims, int cap, int *from_out,
+                             int *to_out, double *prior_out, int *visits_out, double *value_sum_out, int *root_visits, double *root_value_sum) {
+  auto *n = static_cast<network::Network *>(net);
+  auto *g = new game::Game(8, 8);
+  std::stringstream ss;
+  ss << "8 8\n";
+  for (int i = 0; i < 64; ++i) {
+    const char *txt = piece_text(codes[i]);
+    if (txt == nullptr) { delete g; return -1; }
+    ss << i << " - " << txt << "\n";
+  }
+  game::Board *gb = g->board();
+  ss >> gb;
+  if (!white_to_move) {
+    g->_current_player_color = piece::PieceColor::BLACK;
+    gb->_move_count.store(1);   // Board::doMove derives the next colour from the move count's parity (game.cpp:271-276)
+  }
+  g->_moves_since_last_capture = no_capture;
+  g->generatePossibleMoveVectors();
+  auto *root = new tree::Node(g->getCurrentColor());
+  tree::MCTS::expand_node(root, g, n);
+  std::atomic_int iterations{sims}, finished{0};
+  tree::MCTS::mcts(g, n, root, iterations, finished);
+  int k = 0;
+  for (auto &kv : root->_children) {
+    if (k < cap) {
+      from_out[k] = kv.first.startingRow() * 8 + kv.first.startingColumn();
+      to_out[k] = kv.first.endingRow() * 8 + kv.first.endingColumn();
+      prior_out[k] = kv.second->_priority;
+      visits_out[k] = kv.second->_visit_count;
+      value_sum_out[k] = kv.second->_value_sum;
+    }
+    ++k;
+  }
+  *root_visits = root->_visit_count;
+  *root_value_sum = root->_value_sum;
+  delete root;
+  delete g;
+  return k;
+}
+
+// The same search with every playout written down (debugging aid for the GPU-resident search): the loop of
+// tree::MCTS::mcts (tree.cpp:202-262) restated around the reference's own select_optimal_move / expand_node / tryMove /
+// propagate_result. Per playout: trace[0] = plies walked, trace[1 + 2i] = from, trace[2 + 2i] = to, values_out = leaf value,
+// over_out = isOver at the leaf. Stride of `trace` is 20 ints.
+extern "C" int ref_mcts_trace(void *net, const int8_t *codes, int white_to_move, int no_capture, int sims, int *trace, double *values_out,
+                              int *over_out) {
+  auto *n = static_cast<network::Network *>(net);
+  auto *g = new game::Game(8, 8);
+  std::stringstream ss;
+  ss << "8 8\n";
+  for (int i = 0; i < 64; ++i) ss << i << " - " << piece_text(codes[i]) << "\n";
+  game::Board *gb = g->board();
+  ss >> gb;
+  if (!white_to_move) {
+    g->_current_player_color = piece::PieceColor::BLACK;
+    gb->_move_count.store(1);   // Board::doMove derives the next colour from the move count's parity (game.cpp:271-276)
+  }
+  g->_moves_since_last_capture = no_capture;
+  g->generatePossibleMoveVectors();
+  auto *root = new tree::Node(g->getCurrentColor());
+  tree::MCTS::expand_node(root, g, n);
+  for (int s = 0; s < sims; ++s) {
+    tree::Node *node = root;
+    game::Game *clone = g->clone();
+    std::vector<tree::Node *> path = {root};
+    int *t = trace + 20 * s;
+    t[0] = 0;
+    for (int i = 0; i < tree::MCTS::SIMULATION_SEARCH_DEPTH; ++i) {
+      if (clone->isOver()) break;
+      if (!node->expanded()) tree::MCTS::expand_node(node, clone, n);
+      auto optimal = tree::MCTS::select_optimal_move(node);
+      node = optimal.second;
+      t[1 + 2 * t[0]] = optimal.first.startingRow() * 8 + optimal.first.startingColumn();
+      t[2 + 2 * t[0]] = optimal.first.endingRow() * 8 + optimal.first.endingColumn();
+      ++t[0];
+      if (!clone->tryMove(optimal.first)) break;
+      path.push_back(node);
+    }
+    const double cc = clone->getCurrentColor().value();
+    double value;
+    if (clone->isOver()) value = (cc * clone->getResult().evaluate() + 1.0) / 2.0;
+    else {
+      value = clone->board()->score([&](piece::Piece *piece) -> double { return cc * piece->color().value() * piece->type().minimaxValue(); });
+      value = 1.0 / (1.0 + exp(-value / 27.18));
+    }
+    values_out[s] = value;
+    over_out[s] = clone->isOver() ? 1 : 0;
+    tree::MCTS::propagate_result(path, value, clone->getCurrentColor());
+    delete clone;
+  }
+  delete root;
+  delete g;
+  return 0;
 }
