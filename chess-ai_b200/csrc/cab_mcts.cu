@@ -6,10 +6,12 @@
 //   walk kernel  ONE WARP PER TREE. It resumes the tree's parked playouts (virtual loss off, priors formed from the
 //                evaluations of the previous round: K7, tree.cpp:299-306), then launches new ones: PUCT selection with
 //                the children spread over the lanes (tree.cpp:276-283), the move played on the warp's board in shared
-//                memory, and at an unexpanded node the EXPANSION ITSELF: legal moves in the reference's order with
-//                the from-squares spread over the lanes (chess_rules.cuh), child nodes allocated, the parent and the
-//                child boards written straight into the evaluator's input buffer, "opponent has no reply"
-//                (decider.cpp:47-57) decided per child, virtual loss put on the path, playout parked.
+//                memory; at an unexpanded node the playout puts a virtual loss on its path, asks for the expansion and
+//                parks. Playouts of one tree are walked one after the other (each sees the virtual losses of the
+//                ones before it, and the search stays deterministic); the trees run side by side.
+//   expand kernel ONE WARP PER REQUEST: legal moves in the reference's order with the from-squares spread over the
+//                lanes (chess_rules.cuh), child nodes allocated, the parent and the child boards written straight into
+//                the evaluator's input buffer, "opponent has no reply" (decider.cpp:47-57) decided per child.
 //   evaluator    mlp_forward_kernel on the boards queued by the round (cab_api.cu launch_forward), results by slot
 //   game kernel  per game, once all its trees have spent their playouts: roots merged like Node::combineNodes
 //                (tree.cpp:122-142), the move with the best PUCT score played (:195), mate / stalemate / 50-ply rule
@@ -89,6 +91,7 @@ struct Dev {
   GameState *games;
   int n_games, roots, quota, in_flight, max_moves, network_priors, noise, stop_after_search, max_launch;
   int8_t *eval_codes[2]; double *eval_out[2]; int *eval_count[2]; int eval_cap;
+  int *req; int *req_count;             // expansion requests of the round: index of the parked playout that asked
   const double *pf_tbl; int pf_n;       // log((N + 19652 + 1) / 19652) + 1.25 by parent visit count N (host libm)
   const double *sig_tbl;                // 1 / (1 + exp(-m / 27.18)) by material m + 1024 (host libm)
   double exp20;                         // exp(20.0) (host libm): the constant-logit weight of decider.cpp:56
@@ -246,12 +249,42 @@ __device__ __forceinline__ int8_t *make_child(WarpShared *ws, int i) {
   return cb;
 }
 
-// 0: the side to move has no legal move; 1: expansion requested (children allocated, boards queued, *slot set);
-// 2: the evaluation buffer is full this round (try again next round); 3: the tree's arena is full (node stays a leaf)
-__device__ int request_expansion(const Dev &d, int buf, int tree, Node *arena, int node, WarpShared *ws, int *slot) {
+// The expansion a parked playout asked for (Decider::prediction's move loop, decider.cpp:43-58, and Node::expand's
+// children, tree.cpp:86-95): legal moves, child nodes, the parent and the evaluated child boards into the evaluator's
+// input buffer. One warp per request — the requests of a round are independent, so this (the expensive part of a
+// playout: move generation and up to 40 child boards) runs at full occupancy while the tree walk stays sequential per tree.
+//   no legal move           -> the node is marked finished (mate / stalemate); the playout ends when it resumes
+//   evaluation buffer full  -> request dropped; the playout asks again next round
+//   arena full              -> the node stays a leaf for good (state 4)
+__global__ void __launch_bounds__(kWarpsPerCta * 32) mcts_expand_kernel(const Dev d, int buf) {
+  __shared__ WarpShared shared[kWarpsPerCta];
+  const int r = (int) (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5));
+  if (r >= *d.req_count) return;
   const int lane = lane_id();
+  WarpShared *ws = &shared[threadIdx.x >> 5];
+  const int pidx = d.req[r], tree = pidx / d.in_flight;
+  Playout *pl = &d.parked[pidx];
+  Node *arena = d.nodes + (size_t) tree * d.node_cap;
+  const int node = pl->node;
+  {
+    uint16_t *pd = reinterpret_cast<uint16_t *>(&ws->pos);
+    const uint16_t *ps = reinterpret_cast<const uint16_t *>(&pl->pos);
+    for (int i = lane; i < (int) (sizeof(Pos) / 2); i += 32) pd[i] = ps[i];
+  }
+  __syncwarp();
+  Node &parent = arena[node];
   const int n = warp_movegen(ws);
-  if (n <= 0) return 0;
+  if (n <= 0) {                          // Game::updateGameState (game.cpp:872-890): stalemate if the king is safe, else lost
+    if (lane == 0) {
+      const int ks = crules::king_square(ws->pos.sq, ws->pos.side);
+      const bool safe = ks < 0 || !crules::attacked(crules::plain(ws->pos.sq), ks >> 3, ks & 7, ws->pos.side);
+      parent.state = 2;
+      parent.result = safe ? 0 : (int8_t) -ws->pos.side;
+      parent.flags &= (uint8_t) ~kPending;
+      pl->slot = -1;
+    }
+    return;
+  }
   // which children go to the network: all of them, or (decider.cpp:52-57 as shipped) those that leave the opponent no reply
   for (int w = lane; w < kMaxChildren / 32; w += 32) ws->eval_mask[w] = 0;
   __syncwarp();
@@ -271,18 +304,31 @@ __device__ int request_expansion(const Dev &d, int buf, int tree, Node *arena, i
   }
   __syncwarp();
   TreeState *ts = &d.trees[tree];
-  const int first = ts->n_nodes;
-  if ((long) first + n > d.node_cap) {
-    if (lane == 0) atomicAdd(&d.cnt->arena_full, 1ull);
-    return 3;
-  }
-  int s = 0;
+  int first = 0, s = 0;
   if (lane == 0) {
-    s = atomicAdd(d.eval_count[buf], 1 + n_eval);
-    if (s + 1 + n_eval > d.eval_cap) { atomicSub(d.eval_count[buf], 1 + n_eval); atomicAdd(&d.cnt->eval_full, 1ull); s = -1; }
+    first = atomicAdd(&ts->n_nodes, n);
+    if ((long) first + n > d.node_cap) {
+      atomicSub(&ts->n_nodes, n);
+      atomicAdd(&d.cnt->arena_full, 1ull);
+      parent.state = 4;
+      parent.flags &= (uint8_t) ~kPending;
+      pl->slot = -1;
+      first = -1;
+    } else {
+      s = atomicAdd(d.eval_count[buf], 1 + n_eval);
+      if (s + 1 + n_eval > d.eval_cap) {
+        atomicSub(d.eval_count[buf], 1 + n_eval);
+        atomicSub(&ts->n_nodes, n);
+        atomicAdd(&d.cnt->eval_full, 1ull);
+        parent.flags &= (uint8_t) ~kPending;
+        pl->slot = -1;
+        first = -1;
+      }
+    }
   }
+  first = __shfl_sync(0xffffffffu, first, 0);
   s = __shfl_sync(0xffffffffu, s, 0);
-  if (s < 0) return 2;
+  if (first < 0) return;
   // the parent board, then the evaluated children in child order
   int8_t *out = d.eval_codes[buf] + (size_t) s * 64;
   reinterpret_cast<uint16_t *>(out)[lane] = reinterpret_cast<const uint16_t *>(ws->pos.sq)[lane];
@@ -300,11 +346,11 @@ __device__ int request_expansion(const Dev &d, int buf, int tree, Node *arena, i
     }
     rank += __popc(mask);
   }
-  Node &parent = arena[node];
+  const int8_t child_color = (int8_t) -parent.color;
   for (int i = lane; i < n; i += 32) {
     Node c;
     c.prior = 0.0; c.value_sum = 0.0; c.visits = 0; c.vloss = 0; c.first_child = -1; c.n_children = 0;
-    c.color = (int8_t) -parent.color;
+    c.color = child_color;
     c.flags = ((ws->eval_mask[i >> 5] >> (i & 31)) & 1u) ? kEval : 0;
     c.state = 0; c.result = 0;
     c.from = (uint8_t) (ws->moves[i] & 0xff); c.to = (uint8_t) (ws->moves[i] >> 8);
@@ -316,14 +362,11 @@ __device__ int request_expansion(const Dev &d, int buf, int tree, Node *arena, i
   if (lane == 0) {
     parent.first_child = first;
     parent.n_children = (uint16_t) n;
-    parent.flags |= kPending;
-    ts->n_nodes = first + n;
+    parent.state = 1;
+    pl->slot = s;
     atomicAdd(&d.cnt->expansions, 1ull);
     atomicAdd(&d.cnt->boards, (unsigned long long) (1 + n_eval));
   }
-  __syncwarp();
-  *slot = s;
-  return 1;
 }
 
 // priors of a node's children from the evaluations (MCTS::expand_node tree.cpp:294-306 + Node::expand :86-95), the
@@ -372,7 +415,7 @@ struct Walk {                          // the playout in the warp's hands (warp-
 };
 
 // advances the playout until it parks (false) or completes (true); tree.cpp:202-262
-__device__ bool advance(const Dev &d, int buf, int tree, Node *arena, WarpShared *ws, Walk &p) {
+__device__ bool advance(const Dev &d, int tree, Node *arena, WarpShared *ws, Walk &p) {
   const int lane = lane_id();
   Pos *pos = &ws->pos;
   bool truncated = false;
@@ -384,14 +427,12 @@ __device__ bool advance(const Dev &d, int buf, int tree, Node *arena, WarpShared
       __syncwarp();
       break;
     }
+    if (n.state == 4) { truncated = true; break; }        // the arena was full when this node asked: a leaf for good
     if (!(n.flags & kExpanded)) {
       p.slot = -1;
-      if (!(n.flags & kPending)) {     // the first playout to get here asks for the expansion, later ones just wait
-        const int rc = request_expansion(d, buf, tree, arena, p.node, ws, &p.slot);
-        if (rc == 0) { mark_over(pos, &arena[p.node]); break; }
-        if (rc == 3) { truncated = true; break; }
-        if (rc == 1 && lane == 0) arena[p.node].state = 1;
-        __syncwarp();
+      if (!(n.flags & kPending)) {     // the first playout to get here asks for the expansion (slot -2), later ones just wait
+        if (lane == 0) n.flags |= kPending;
+        p.slot = -2;
       }
       if (lane < p.path_len) { Node &v = arena[ws->path[lane]]; v.visits += 1; v.vloss += 1; }   // virtual loss on the path
       __syncwarp();
@@ -451,7 +492,10 @@ __device__ void park(const Dev &d, int tree, WarpShared *ws, const Walk &p, int 
   const uint16_t *ps = reinterpret_cast<const uint16_t *>(&ws->pos);
   for (int i = lane; i < (int) (sizeof(Pos) / 2); i += 32) pd[i] = ps[i];
   if (lane < kDepth + 2) dst->path[lane] = ws->path[lane];
-  if (lane == 0) { dst->node = p.node; dst->depth = p.depth; dst->path_len = p.path_len; dst->slot = p.slot; }
+  if (lane == 0) {
+    dst->node = p.node; dst->depth = p.depth; dst->path_len = p.path_len; dst->slot = p.slot;
+    if (p.slot == -2) d.req[atomicAdd(d.req_count, 1)] = tree * d.in_flight + at;    // the expansion kernel's work list
+  }
   __syncwarp();
 }
 __device__ void unpark(const Dev &d, int tree, WarpShared *ws, Walk &p, int at) {
@@ -492,7 +536,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) mcts_walk_kernel(const Dev 
   Walk p;
   for (int i = 0; i < n_parked; ++i) {
     unpark(d, tree, ws, p, i);
-    if (advance(d, buf, tree, arena, ws, p)) ++done;
+    if (advance(d, tree, arena, ws, p)) ++done;
     else park(d, tree, ws, p, kept++);
   }
   // (3) new playouts (one at a time until the root exists)
@@ -509,7 +553,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) mcts_walk_kernel(const Dev 
     __syncwarp();
     p.node = 0; p.depth = 0; p.path_len = 1; p.slot = -1;
     ++launched;
-    if (advance(d, buf, tree, arena, ws, p)) ++done;
+    if (advance(d, tree, arena, ws, p)) ++done;
     else park(d, tree, ws, p, kept++);
   }
   if (lane == 0) { ts->n_parked = kept; ts->done = done; ts->launched = launched; }
@@ -668,6 +712,7 @@ struct cab_mcts {
 
 static void mcts_free(cab_mcts *q) {
   if (!q) return;
+  cudaFree(q->d.req); cudaFree(q->d.req_count);
   cudaFree(q->d.nodes); cudaFree(q->d.trees); cudaFree(q->d.parked); cudaFree(q->d.games); cudaFree(q->d.cnt); cudaFree(q->d.cases);
   for (int b = 0; b < 2; ++b) { cudaFree(q->d.eval_codes[b]); cudaFree(q->d.eval_out[b]); cudaFree(q->d.eval_count[b]); }
   cudaFree(q->d_pf); cudaFree(q->d_sig);
@@ -691,6 +736,9 @@ static int mcts_build(cab_mcts *q) {
   CAB_CUDA(cudaMalloc(&d.trees, trees * sizeof(TreeState)));
   CAB_CUDA(cudaMalloc(&d.parked, (size_t) trees * p.in_flight * sizeof(Playout)));
   CAB_CUDA(cudaMalloc(&d.games, p.games * sizeof(GameState)));
+  CAB_CUDA(cudaMalloc(&d.req, (size_t) trees * p.in_flight * sizeof(int)));
+  CAB_CUDA(cudaMalloc(&d.req_count, sizeof(int)));
+  CAB_CUDA(cudaMemset(d.req_count, 0, sizeof(int)));
   CAB_CUDA(cudaMalloc(&d.cnt, sizeof(Counters)));
   CAB_CUDA(cudaMemset(d.cnt, 0, sizeof(Counters)));
   d.cases_cap = p.save_ratio > 0.0 ? (int) std::min<long>((long) p.games * (p.max_moves + 1), 1L << 24) : 1;
@@ -804,13 +852,16 @@ int cab_mcts_run(cab_mcts *q, int search_only, long max_rounds, cab_mcts_stats *
     const int buf = q->round_parity;
     mcts_game_kernel<<<(d.n_games + 127) / 128, 128, 0, q->stream>>>(d);
     CAB_CUDA(cudaMemsetAsync(d.eval_count[buf], 0, sizeof(int), q->stream));
+    CAB_CUDA(cudaMemsetAsync(d.req_count, 0, sizeof(int), q->stream));
     mcts_walk_kernel<<<(n_trees + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, q->stream>>>(d, buf);
+    // one warp per request; the grid covers the most a round can ask for, warps beyond the count leave at once
+    mcts_expand_kernel<<<(n_trees * d.in_flight + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, q->stream>>>(d, buf);
     CAB_CUDA(cudaGetLastError());
     CAB_CUDA(cudaMemcpyAsync(q->h_count, d.eval_count[buf], sizeof(int), cudaMemcpyDeviceToHost, q->stream));
     CAB_CUDA(cudaMemcpyAsync(&h, d.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, q->stream));
     CAB_CUDA(cudaStreamSynchronize(q->stream));
     const int n_boards = *q->h_count;
-    net->launches += 2;
+    net->launches += 3;
     ++rounds;
     q->round_parity ^= 1;
     if (n_boards > 0) {
