@@ -67,6 +67,7 @@ _SIGS = {
     "cab_leafq_pending": [_vp, _lp],
     "cab_leafq_set_precision": [_vp, C.c_int],
     "cab_prediction_host": [_vp, _i8p, C.c_int, C.c_int, _dp, C.POINTER(C.c_int), _f64p, C.c_int, _ip],
+    "cab_best_move_host": [_vp, _i8p, C.c_int, C.c_int, C.c_double, _ip, _ip, _dp, _ip, _ip],
     "cab_leafq_flush": [_vp, _lp],
     "cab_leafq_flush_async": [_vp, _lp],
     "cab_leafq_wait": [_vp],
@@ -572,6 +573,15 @@ class SelfPlay:
         codes, targets = np.zeros((max(n.value, 1), 64), np.int8), np.zeros(max(n.value, 1))
         _ck(lib().cab_mcts_cases(self._h, codes.ctypes.data, targets.ctypes.data, n.value, C.byref(n)))
         return codes[:n.value], targets[:n.value]
+
+
+def best_move(net, codes64, side, precision="fp64", tol=0.0):
+    """First-ranked move under the network (argmax of net(child), first wins): (from, to, value, n_moves, n_refined)."""
+    fr, to, nm, nr, val = C.c_int(-1), C.c_int(-1), C.c_int(0), C.c_int(0), C.c_double(0)
+    _ck(lib().cab_best_move_host(net._h, np.ascontiguousarray(codes64, dtype=np.int8).reshape(64), int(side),
+                                 {"fp64": 0, "f16": 1, "bf16": 2}[precision], float(tol), C.byref(fr), C.byref(to), C.byref(val), C.byref(nm),
+                                 C.byref(nr)))
+    return fr.value, to.value, val.value, nm.value, nr.value
 
 
 def device_movegen(codes, side, queen_only=False, cap=256, no_reply=False, device=0):

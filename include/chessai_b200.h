@@ -130,6 +130,14 @@ CAB_API int cab_leafq_stats(cab_leafq *q, long *launches, long *flushes, long *e
  * then cm * net(child)); 1: cm * net(child) for every move. *n_moves = number of keys (may exceed cap: truncated). */
 CAB_API int cab_prediction_host(cab_net *net, const int8_t *codes64, int side_to_move, int network_priors, double *eval_out,
                         int *moves_out, double *logits_out, int cap, int *n_moves);
+/* The move the network ranks first (first child in std::map order with the greatest net(child): the weight of a move
+ * is exp(cm * logit) = exp(net(child)), decider.cpp:52-56 + tree.cpp:302), with the reduced-precision evaluators made
+ * safe for ranking: precision 0 = fp64 (the reference answer); 1 = fused fp16 tcgen05; 2 = bf16 tcgen05 (wide nets).
+ * For 1 / 2 every child within `tol` of the reduced-precision maximum is re-evaluated in fp64 and the maximum taken
+ * over the refined values, so the move is IDENTICAL to the fp64 choice whenever the reduced path errs by <= tol / 2
+ * per board (tol <= 0: 0.1 for fp16, 0.3 for bf16 = twice the stated tolerances). *n_refined = boards redone in fp64. */
+CAB_API int cab_best_move_host(cab_net *net, const int8_t *codes64, int side_to_move, int precision, double tol, int *from_out,
+                               int *to_out, double *value_out, int *n_moves, int *n_refined);
 CAB_API int cab_prior_softmax_host(int device, const double *logits, const int *seg_off, int n_seg, const double *color_mult,
                                    double *priors_out);
 

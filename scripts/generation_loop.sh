@@ -17,7 +17,7 @@ PY
 NET=$WORK/start.txt
 for g in $(seq 1 $G); do
   SHARD=$WORK/gen$g.shard
-  $L/selfplay $NET $GAMES $PLAYOUTS $MOVES $(nproc) 256 1 0 $((1000 + g)) $SHARD 1.0 fp64 4
+  $L/selfplay $NET $GAMES $PLAYOUTS $MOVES - 8 1 0 $((1000 + g)) $SHARD 1.0 fp64 4
   $L/train $NET $SHARD $WORK/network_dump batch $STEPS $BATCH 0 $g 100
   NET=$WORK/network_dump/latest.txt
 done

@@ -146,23 +146,24 @@ def test_virtual_loss_batches_many_boards_per_flush(cab, golden, tmp_path):
     assert r["flushes"] < r["expansions"] / 8                   # many expansions share one GPU round trip
 
 
-def test_selfplay_driver_on_the_fast_rules_engine(cab, golden, tmp_path):
-    """chess-ai_b200/host/selfplay.cpp: many games, per-thread leaf queues, virtual loss; bookkeeping must add up."""
+def test_selfplay_driver(cab, golden, tmp_path):
+    """chess-ai_b200/host/selfplay.cpp, the command-line driver of the device-resident search: bookkeeping must add up."""
     exe = os.path.join(ROOT, "chess-ai_b200", "lib", "selfplay")
     if not os.path.exists(exe):
         pytest.skip("selfplay not built")
     latest = str(tmp_path / "latest.txt")
     cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"]).dump(latest)
-    out = subprocess.check_output([exe, latest, "32", "60", "2", "4", "64", "1"], timeout=300)
+    out = subprocess.check_output([exe, latest, "32", "60", "2", "-", "8", "1"], timeout=300)
     r = json.loads(out.decode().strip().splitlines()[-1])
-    assert r["moves_played"] == 32 * 2 and r["playouts"] == 32 * 2 * 60
+    assert r["moves_played"] == 32 * 2 and r["playouts"] == 32 * 2 * 60 and r["games_finished"] == 32
     assert r["boards_evaluated"] > r["expansions"] * 15           # parent + ~20-30 children per expansion
     assert r["avg_boards_per_flush"] > 500 and r["flushes"] < r["expansions"] / 10
+    assert r["arena_full"] == 0 and r["eval_full"] == 0
     # the reference's default search shape: 4 root-parallel trees of 125 playouts, merged like Node::combineNodes
-    out4 = subprocess.check_output([exe, latest, "16", "500", "2", "4", "64", "1", "0", "7", "-", "0", "fp64", "4"], timeout=300)
+    out4 = subprocess.check_output([exe, latest, "16", "500", "2", "-", "8", "1", "0", "7", "-", "0", "fp64", "4"], timeout=300)
     r4 = json.loads(out4.decode().strip().splitlines()[-1])
     assert r4["roots"] == 4 and r4["moves_played"] == 16 * 2 and r4["playouts"] == 16 * 2 * 4 * 125
-    out0 = subprocess.check_output([exe, latest, "8", "40", "1", "2", "16", "0"], timeout=300)   # shipped inverted priors
+    out0 = subprocess.check_output([exe, latest, "8", "40", "1", "-", "4", "0"], timeout=300)   # shipped inverted priors
     r0 = json.loads(out0.decode().strip().splitlines()[-1])
     assert r0["playouts"] == 8 * 40 and r0["boards_evaluated"] == r0["expansions"]               # only the parent board
 

@@ -36,7 +36,7 @@ def latest(cab, tmp_path_factory):
 @pytest.fixture(scope="module")
 def shard(latest, tmp_path_factory):
     path = str(tmp_path_factory.mktemp("cases") / "selfplay.shard")
-    r = run(os.path.join(LIBDIR, "selfplay"), latest, 48, 40, 12, 4, 64, 1, 0, 99, path, 1.0)
+    r = run(os.path.join(LIBDIR, "selfplay"), latest, 48, 40, 12, "-", 8, 1, 0, 99, path, 1.0)
     assert r["cases_written"] == r["moves_played"] == 48 * 12            # ratio 1.0 keeps every board
     return path
 
@@ -54,7 +54,7 @@ def test_selfplay_cases_follow_the_target_rule(shard):
 
 def test_sampling_ratio(latest, tmp_path):
     path = str(tmp_path / "tenth.shard")
-    r = run(os.path.join(LIBDIR, "selfplay"), latest, 64, 20, 10, 4, 64, 0, 0, 7, path)      # default ratio 0.1
+    r = run(os.path.join(LIBDIR, "selfplay"), latest, 64, 20, 10, "-", 4, 0, 0, 7, path)      # default ratio 0.1
     assert 20 <= r["cases_written"] <= 120 and os.path.getsize(path) == 72 * r["cases_written"]   # 640 moves * 0.1 +- 5 sigma
 
 
