@@ -83,6 +83,8 @@ _SIGS = {
     "cab_train_sequence": [_vp, _i8p, _f64p, C.c_long, _dp, C.c_uint64, _vp, _ip],
     "cab_train_batch_host": [_vp, _i8p, _f64p, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp],
     "cab_train_batch_dev": [_vp, _vp, _vp, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp, _vp],
+    "cab_train_epoch_dev": [_vp, _vp, _vp, C.c_long, C.c_long, _dp, C.c_double, C.c_double, C.c_int, C.c_uint64, _vp, _vp, _vp],
+    "cab_train_epoch_bf16_dev": [_vp, _vp, _vp, C.c_long, C.c_long, _dp, C.c_double, C.c_double, C.c_int, C.c_uint64, _vp, _vp, _vp],
     "cab_dropout": [_vp, C.c_double, C.c_uint64, C.c_uint64, _lp],
     "cab_dp_unique_id": [_vp],
     "cab_dp_init": [_vp, _vp, C.c_int, C.c_int],
@@ -445,6 +447,28 @@ class Optimizer:
         lam_c, acc, e0, e1 = C.c_double(lam), C.c_int(0), C.c_double(0), C.c_double(0)
         _ck(lib().cab_train_batch_bf16_host(network._h, c.reshape(-1), t, len(c), C.byref(lam_c), max_const, rate, C.byref(acc), C.byref(e0), C.byref(e1)))
         return lam_c.value, bool(acc.value), e0.value, e1.value
+
+
+class TrainStats(C.Structure):
+    _fields_ = [("steps", C.c_long), ("accepted", C.c_long), ("resets", C.c_int), ("last_accepted", C.c_int), ("first_err", C.c_double),
+                ("last_err", C.c_double), ("last_new_err", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def train_epoch_dev(network, codes_dev_ptr, targets_dev_ptr, n_cases, batch, lam, max_const=15.0, rate=1.1, reset_rule=True, dropout_seed=0x5EED,
+                    trace=False, stream=0, bf16=False):
+    """train_network's loop (train.cpp:39-68) over resident cases as consecutive minibatches, decisions on the device, one
+    wait at the end. Returns (lambda, stats dict[, trace of (E, E') per step])."""
+    st = TrainStats()
+    steps = (n_cases + batch - 1) // batch
+    tr = np.zeros((steps, 2)) if trace else None
+    lam_c = C.c_double(lam)
+    fn = lib().cab_train_epoch_bf16_dev if bf16 else lib().cab_train_epoch_dev
+    _ck(fn(network._h, codes_dev_ptr, targets_dev_ptr, n_cases, batch, C.byref(lam_c), max_const, rate, 1 if reset_rule else 0, dropout_seed,
+           C.byref(st), None if tr is None else tr.ctypes.data, stream))
+    return (lam_c.value, st.as_dict(), tr) if trace else (lam_c.value, st.as_dict())
 
 
 # ---- network::NetworkStorage ----------------------------------------------------------------------------------------

@@ -557,7 +557,7 @@ int cab_net_destroy(cab_net *net) {
   }
   free_plan(&net->fwd); free_plan(&net->bwd);
   cudaFree(net->d_w); cudaFree(net->d_dw); cudaFree(net->d_grad); cudaFree(net->d_acts); cudaFree(net->d_psis);
-  cudaFree(net->d_tcodes); cudaFree(net->d_ttargets); cudaFree(net->d_tout); cudaFree(net->d_tout_tc); cudaFree(net->d_scalars);
+  cudaFree(net->d_tcodes); cudaFree(net->d_ttargets); cudaFree(net->d_tout); cudaFree(net->d_tout_tc); cudaFree(net->d_scalars); cudaFree(net->d_ctl);
   if (net->train_stream) cudaStreamDestroy(net->train_stream);
   for (int i = 0; i < 4; ++i) if (net->aux_stream[i]) cudaStreamDestroy(net->aux_stream[i]);
   for (int i = 0; i < 5; ++i) if (net->aux_event[i]) cudaEventDestroy(net->aux_event[i]);

@@ -119,6 +119,7 @@ struct cab_net {
   long tout_cap = 0;
   long tbuf_cap = 0;
   double *d_scalars = nullptr; // small device scratch (lambda, flags ...)
+  void *d_ctl = nullptr;       // cab::TrainCtl: the minibatch trainer's lambda / decision / counters, resident on the device
   cudaStream_t train_stream = nullptr;
   cudaStream_t aux_stream[4] = {};  // helper streams for fanned-out passes (cab_train.cu:fan_out)
   cudaEvent_t aux_event[5] = {};

@@ -83,6 +83,10 @@ static int ensure_train_state(cab_net *net) {
     CAB_CUDA(cudaMalloc(&net->d_scalars, 64 * sizeof(double)));
     CAB_CUDA(cudaMemset(net->d_scalars, 0, 64 * sizeof(double)));
   }
+  if (net->d_ctl == nullptr) {
+    CAB_CUDA(cudaMalloc(&net->d_ctl, sizeof(TrainCtl)));
+    CAB_CUDA(cudaMemset(net->d_ctl, 0, sizeof(TrainCtl)));
+  }
   return CAB_OK;
 }
 
@@ -309,21 +313,18 @@ static int ensure_tout(cab_net *net, long n) {   // bf16 mode: only the output b
   return CAB_OK;
 }
 
-static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d_targets, long n, double *lambda,
-                            double max_const, double rate, int *accepted, double *err, double *new_err,
-                            cudaStream_t stream, bool bf16 = false) {
-  if (!bf16 && !net->fp64_ok) { set_error("layer too wide for the fp64 training kernels"); return CAB_EINVAL; }
-  if (bf16 && !tc_fits(net)) { set_error("bf16 tcgen05 training needs hidden widths that are multiples of 256"); return CAB_EINVAL; }
-  int rc = ensure_train_state(net);
+// One minibatch step, ENQUEUED on `stream` and left there: forward with saved activations, backward, gradient,
+// (all-reduce), update with the device-resident lambda, re-forward, E', (all-reduce), decision + rollback + reset rule
+// on the device (decide_kernel ...). Nothing here waits for the GPU: consecutive steps queue up behind each other.
+static int enqueue_step(cab_net *net, const int8_t *d_codes, const double *d_targets, long n, cudaStream_t stream, bool bf16,
+                        double *d_e_trace) {
+  int rc = bf16 ? ensure_tout(net, n) : ensure_batch_buffers(net, n);
   if (rc != CAB_OK) return rc;
-  std::unique_lock<std::mutex> turn(net->tc_mu, std::defer_lock);
-  if (bf16) {   // the bf16 path's scratch is per net: this step takes its turn (cab_tc.cu)
-    turn.lock();
-    if ((rc = tc_turn_begin(net, stream)) != CAB_OK) return rc;
-  }
-  if ((rc = bf16 ? ensure_tout(net, n) : ensure_batch_buffers(net, n)) != CAB_OK) return rc;
   double *d_tout = bf16 ? net->d_tout_tc : net->d_tout;
+  TrainCtl *ctl = static_cast<TrainCtl *>(net->d_ctl);
   const long nw = net->n_weights;
+  const int ew_grid = (int) std::min<long>((nw + 255) / 256, 148L * 8);
+  net->pack_dirty = net->tc_dirty = net->f16_dirty = true;     // the previous step may have rolled back or diluted the weights
   if (!bf16) {
     std::lock_guard<std::mutex> lk(net->mu);
     if ((rc = ensure_packed(net, stream, false)) != CAB_OK) return rc;
@@ -345,7 +346,7 @@ static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d
     int nrc = g_nccl.AllReduce(net->d_grad, net->d_grad, (size_t) nw + 4, kNcclDouble, kNcclSum, net->nccl_comm, stream);
     if (nrc != 0) return nccl_fail(nrc, "ncclAllReduce(grad)");
   }
-  apply_update_kernel<<<(int) std::min<long>((nw + 255) / 256, 148L * 8), 256, 0, stream>>>(net->d_w, net->d_dw, net->d_grad, nw, *lambda);
+  apply_update_ctl_kernel<<<ew_grid, 256, 0, stream>>>(net->d_w, net->d_dw, net->d_grad, nw, ctl);
   net->launches += 2;
   net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   // re-forward (network.cpp:265) and E'
@@ -363,31 +364,85 @@ static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d
   }
   CAB_CUDA(cudaMemsetAsync(net->d_scalars, 0, 2 * sizeof(double), stream));
   batch_error_kernel<<<(int) std::min<long>((n + 255) / 256, 148L * 4), 256, 0, stream>>>(d_tout, d_targets, n, net->d_scalars);
-  net->launches++;
   if (net->nccl_comm != nullptr) {
     int nrc = g_nccl.AllReduce(net->d_scalars, net->d_scalars, 1, kNcclDouble, kNcclSum, net->nccl_comm, stream);
     if (nrc != 0) return nccl_fail(nrc, "ncclAllReduce(E')");
   }
-  double h_first[3] = {0, 0, 0}, h_new = 0;
-  CAB_CUDA(cudaMemcpyAsync(h_first, net->d_grad + nw, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
-  CAB_CUDA(cudaMemcpyAsync(&h_new, net->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, stream));
-  CAB_CUDA(cudaStreamSynchronize(stream));
-  const double count = h_first[2];
-  const double e0 = h_first[0] / count, e1 = h_new / count;
-  const bool ok = e1 < e0;                                    // network.cpp:269
-  if (ok) {
-    if (*lambda < max_const) *lambda *= rate;                 // :270-271
-  } else {
-    *lambda /= rate;                                          // :273
-    rollback_kernel<<<(int) std::min<long>((nw + 255) / 256, 148L * 8), 256, 0, stream>>>(net->d_w, net->d_dw, nw);
-    net->launches++;
-    net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
-    CAB_CUDA(cudaGetLastError());
+  decide_kernel<<<1, 1, 0, stream>>>(ctl, net->d_grad + nw, net->d_scalars, d_e_trace);                     // network.cpp:269-273, train.cpp:54-57
+  rollback_ctl_kernel<<<ew_grid, 256, 0, stream>>>(net->d_w, net->d_dw, nw, ctl);                           // :274-277 when rejected
+  dropout_ctl_kernel<<<ew_grid, 256, 0, stream>>>(net->d_w, nw, 0.01, ctl);                                 // only behind a lambda reset
+  net->launches += 4;
+  net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
+  CAB_CUDA(cudaGetLastError());
+  return CAB_OK;
+}
+
+static int upload_ctl(cab_net *net, double lambda, double max_const, double rate, int reset_rule, uint64_t seed, cudaStream_t stream) {
+  TrainCtl h;
+  memset(&h, 0, sizeof h);
+  h.lambda = lambda; h.max_const = max_const; h.rate = rate; h.reset_rule = reset_rule; h.seed = seed;
+  CAB_CUDA(cudaMemcpyAsync(net->d_ctl, &h, sizeof h, cudaMemcpyHostToDevice, stream));   // (pageable source: staged before the call returns)
+  return CAB_OK;
+}
+
+// the one-step entry points: upload lambda, one step, wait, hand the decision back (Optimizer::optimize's signature)
+static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d_targets, long n, double *lambda,
+                            double max_const, double rate, int *accepted, double *err, double *new_err,
+                            cudaStream_t stream, bool bf16 = false) {
+  if (!bf16 && !net->fp64_ok) { set_error("layer too wide for the fp64 training kernels"); return CAB_EINVAL; }
+  if (bf16 && !tc_fits(net)) { set_error("bf16 tcgen05 training needs hidden widths that are multiples of 256"); return CAB_EINVAL; }
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  std::unique_lock<std::mutex> turn(net->tc_mu, std::defer_lock);
+  if (bf16) {   // the bf16 path's scratch is per net: this step takes its turn (cab_tc.cu)
+    turn.lock();
+    if ((rc = tc_turn_begin(net, stream)) != CAB_OK) return rc;
   }
-  if (accepted) *accepted = ok ? 1 : 0;
-  if (err) *err = e0;
-  if (new_err) *new_err = e1;
+  if ((rc = upload_ctl(net, *lambda, max_const, rate, 0, 0, stream)) != CAB_OK) return rc;
+  if ((rc = enqueue_step(net, d_codes, d_targets, n, stream, bf16, nullptr)) != CAB_OK) return rc;
+  TrainCtl h;
+  CAB_CUDA(cudaMemcpyAsync(&h, net->d_ctl, sizeof h, cudaMemcpyDeviceToHost, stream));
   if (bf16 && (rc = tc_turn_end(net, stream)) != CAB_OK) return rc;
+  CAB_CUDA(cudaStreamSynchronize(stream));
+  *lambda = h.lambda;
+  if (accepted) *accepted = h.ok;
+  if (err) *err = h.e0;
+  if (new_err) *new_err = h.e1;
+  return CAB_OK;
+}
+
+// n_total cases as consecutive minibatches of `batch` (the last one may be shorter), every step enqueued behind the
+// previous one, ONE wait at the end: train_network's loop (train.cpp:39-68) over a resident shard without the host in it.
+static int train_epoch_impl(cab_net *net, const int8_t *d_codes, const double *d_targets, long n_total, long batch, double *lambda,
+                            double max_const, double rate, int reset_rule, uint64_t seed, cab_train_stats *stats, double *e_trace_host,
+                            cudaStream_t stream, bool bf16) {
+  if (!bf16 && !net->fp64_ok) { set_error("layer too wide for the fp64 training kernels"); return CAB_EINVAL; }
+  if (bf16 && !tc_fits(net)) { set_error("bf16 tcgen05 training needs hidden widths that are multiples of 256"); return CAB_EINVAL; }
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  std::unique_lock<std::mutex> turn(net->tc_mu, std::defer_lock);
+  if (bf16) {
+    turn.lock();
+    if ((rc = tc_turn_begin(net, stream)) != CAB_OK) return rc;
+  }
+  const long steps = (n_total + batch - 1) / batch;
+  struct DevBuf { double *p = nullptr; ~DevBuf() { cudaFree(p); } } trace;
+  if (e_trace_host != nullptr) CAB_CUDA(cudaMalloc(&trace.p, (size_t) steps * 2 * sizeof(double)));
+  if ((rc = upload_ctl(net, *lambda, max_const, rate, reset_rule, seed, stream)) != CAB_OK) return rc;
+  for (long st = 0; st < steps; ++st) {
+    const long b0 = st * batch, nb = std::min(batch, n_total - b0);
+    if ((rc = enqueue_step(net, d_codes + b0 * 64, d_targets + b0, nb, stream, bf16, trace.p)) != CAB_OK) return rc;
+  }
+  TrainCtl h;
+  CAB_CUDA(cudaMemcpyAsync(&h, net->d_ctl, sizeof h, cudaMemcpyDeviceToHost, stream));
+  if (e_trace_host != nullptr) CAB_CUDA(cudaMemcpyAsync(e_trace_host, trace.p, (size_t) steps * 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (bf16 && (rc = tc_turn_end(net, stream)) != CAB_OK) return rc;
+  CAB_CUDA(cudaStreamSynchronize(stream));
+  *lambda = h.lambda;
+  if (stats) {
+    stats->steps = (long) h.steps; stats->accepted = (long) h.accepted; stats->resets = h.resets;
+    stats->first_err = h.e_first; stats->last_err = h.e0; stats->last_new_err = h.e1; stats->last_accepted = h.ok;
+  }
   return CAB_OK;
 }
 
@@ -511,6 +566,28 @@ int cab_train_batch_host(cab_net *net, const int8_t *codes, const double *target
   CAB_CUDA(cudaMemcpyAsync(net->d_tcodes, codes, n * 64, cudaMemcpyHostToDevice, s));
   CAB_CUDA(cudaMemcpyAsync(net->d_ttargets, targets, n * sizeof(double), cudaMemcpyHostToDevice, s));
   return train_batch_impl(net, net->d_tcodes, net->d_ttargets, n, lambda, max_const, rate, accepted, err, new_err, s);
+}
+
+int cab_train_epoch_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases, long batch, double *lambda,
+                        double max_const, double rate, int reset_rule, uint64_t dropout_seed, cab_train_stats *stats, double *e_trace_host,
+                        void *stream) {
+  if (!net || !lambda || n_cases <= 0 || batch <= 0 || !codes_dev || !targets_dev) { set_error("bad argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  return train_epoch_impl(net, codes_dev, targets_dev, n_cases, batch, lambda, max_const, rate, reset_rule, dropout_seed, stats, e_trace_host,
+                          stream ? (cudaStream_t) stream : net->train_stream, false);
+}
+
+int cab_train_epoch_bf16_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases, long batch, double *lambda,
+                             double max_const, double rate, int reset_rule, uint64_t dropout_seed, cab_train_stats *stats, double *e_trace_host,
+                             void *stream) {
+  if (!net || !lambda || n_cases <= 0 || batch <= 0 || !codes_dev || !targets_dev) { set_error("bad argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  return train_epoch_impl(net, codes_dev, targets_dev, n_cases, batch, lambda, max_const, rate, reset_rule, dropout_seed, stats, e_trace_host,
+                          stream ? (cudaStream_t) stream : net->train_stream, true);
 }
 
 int cab_train_batch_bf16_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n, double *lambda,

@@ -442,6 +442,67 @@ __global__ void __launch_bounds__(256) apply_update_kernel(double *__restrict__ 
     w[i] += d;
   }
 }
+// ---- the minibatch step's decision, on the device (no host round trip inside a step) -----------------------------------
+struct TrainCtl {              // device-resident state of the minibatch trainer
+  double lambda, max_const, rate;
+  double e0, e1;               // batch-mean E and E' of the last step
+  double e_first;              // E of the first step since the state was reset
+  int ok;                      // last step accepted
+  int reset_rule;              // train.cpp:54-57 after every step: lambda outside [1e-4, 10] -> lambda = 2, dropout
+  int do_dropout;              // set by decide for the dropout kernel that follows
+  int resets;
+  long long accepted, steps;
+  unsigned long long seed;     // Philox key of the dropout
+};
+// dW = (lambda / count) * G ; W += dW with lambda read on the device
+__global__ void __launch_bounds__(256) apply_update_ctl_kernel(double *__restrict__ w, double *__restrict__ dw, const double *__restrict__ grad,
+                                                                long n, const TrainCtl *__restrict__ ctl) {
+  const double scale = ctl->lambda / grad[n + 2];
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+    const double d = grad[i] * scale;
+    dw[i] = d;
+    w[i] += d;
+  }
+}
+// E' < E ? accept (lambda *= rate while lambda < max_const) : reject (lambda /= rate; the rollback kernel undoes the update)
+// (network.cpp:269-278), then the train loop's reset rule (train.cpp:54-57). grad_tail = {sum E, -, count}; e1_sum = sum E'.
+__global__ void decide_kernel(TrainCtl *ctl, const double *grad_tail, const double *e1_sum, double *e_trace) {
+  const double count = grad_tail[2];
+  const double e0 = grad_tail[0] / count, e1 = *e1_sum / count;
+  const bool ok = e1 < e0;
+  double lam = ctl->lambda;
+  if (ok) { if (lam < ctl->max_const) lam *= ctl->rate; }
+  else lam /= ctl->rate;
+  ctl->do_dropout = 0;
+  if (ctl->reset_rule && (lam < 0.0001 || 10.0 < lam)) {
+    lam = 2.0;
+    ctl->do_dropout = 1;
+    ctl->resets += 1;
+  }
+  if (e_trace != nullptr) { e_trace[2 * ctl->steps] = e0; e_trace[2 * ctl->steps + 1] = e1; }
+  if (ctl->steps == 0) ctl->e_first = e0;
+  ctl->lambda = lam;
+  ctl->e0 = e0; ctl->e1 = e1;
+  ctl->ok = ok ? 1 : 0;
+  ctl->accepted += ok ? 1 : 0;
+  ctl->steps += 1;
+}
+__global__ void __launch_bounds__(256) rollback_ctl_kernel(double *__restrict__ w, const double *__restrict__ dw, long n,
+                                                            const TrainCtl *__restrict__ ctl) {
+  if (ctl->ok) return;
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) w[i] -= dw[i];
+}
+// Optimizer::dropout behind the reset rule: weight i is replaced w.p. 0.01 by U(-1,1), Philox(seed, offset = reset index)
+__global__ void __launch_bounds__(256) dropout_ctl_kernel(double *__restrict__ w, long n, double rate, const TrainCtl *__restrict__ ctl) {
+  if (!ctl->do_dropout) return;
+  const unsigned long long offset = (unsigned long long) (ctl->resets - 1), seed = ctl->seed;
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t) i, (uint32_t) ((uint64_t) i >> 32), (uint32_t) offset, (uint32_t) (offset >> 32), (uint32_t) seed, (uint32_t) (seed >> 32), r);
+    if (u53(r[0], r[1]) < rate) w[i] = 2.0 * u53(r[2], r[3]) + -1.0;
+  }
+}
+
 // W -= dW   (network.cpp:274-277)
 __global__ void __launch_bounds__(256) rollback_kernel(double *__restrict__ w, const double *__restrict__ dw, long n) {
   for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) w[i] -= dw[i];

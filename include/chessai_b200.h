@@ -224,6 +224,22 @@ CAB_API int cab_train_batch_host(cab_net *net, const int8_t *codes_host, const d
 CAB_API int cab_train_batch_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases,
                         double *lambda, double max_const, double rate, int *accepted, double *err, double *new_err,
                         void *stream);
+/* train_network's loop (train.cpp:39-68) over n_cases RESIDENT cases as consecutive minibatches of `batch` (the last may be
+ * shorter) with NO host round trip inside: lambda, the accept / reject decision, the rollback and (reset_rule != 0) the
+ * lambda-reset + dropout rule of train.cpp:54-57 live on the device; every step is enqueued behind the previous one and
+ * the call waits once, at the end. Identical arithmetic to calling cab_train_batch_dev per minibatch (tests).
+ * e_trace_host (optional): 2 doubles per step (E, E'). */
+typedef struct cab_train_stats {
+  long steps, accepted;
+  int resets, last_accepted;
+  double first_err, last_err, last_new_err;
+} cab_train_stats;
+CAB_API int cab_train_epoch_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases, long batch,
+                                double *lambda, double max_const, double rate, int reset_rule, uint64_t dropout_seed,
+                                cab_train_stats *stats, double *e_trace_host, void *stream);
+CAB_API int cab_train_epoch_bf16_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases, long batch,
+                                     double *lambda, double max_const, double rate, int reset_rule, uint64_t dropout_seed,
+                                     cab_train_stats *stats, double *e_trace_host, void *stream);
 /* The same minibatch step on the bf16 tcgen05 path, for WIDE nets (hidden widths multiples of 256; BASELINE.json
  * configs[4]): forward with saved activations, dX and dW as tensor-core GEMMs (fp32 accumulate, psi kept in bf16),
  * gradient in fp64, update / re-forward / accept-or-roll-back exactly as above on the fp64 master weights.

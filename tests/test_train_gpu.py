@@ -179,3 +179,44 @@ def test_full_size_batch_update_is_the_weighted_mean_of_its_halves(cab, golden):
     mix = (n_a * d_a + (n - n_a) * d_b) / n
     assert np.linalg.norm(d_all) > 0 and np.linalg.norm(d_all - mix) <= 1e-9 * np.linalg.norm(d_all)
     assert abs(e_all - (n_a * e_a + (n - n_a) * e_b) / n) <= 1e-12 * e_all
+
+
+def test_epoch_on_the_device_equals_step_by_step(cab, golden):
+    """cab_train_epoch_dev (lambda, accept / reject, rollback and the reset + dropout rule on the device, one wait at the
+    end) against the same minibatches pushed one by one through cab_train_batch_dev with the host deciding in between."""
+    import ctypes as C
+    import torch
+    synth = importlib.import_module("chess-ai_b200.synth")
+    n, batch = 6 * 4096 + 1000, 4096                         # a short last minibatch too
+    codes = synth.synthetic_boards(n, seed=5)
+    teacher = cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"])
+    targets = teacher.predict_batch(codes)
+    w0 = cab.Network.randomNetwork(DEFAULT_DIMS, seed=77).get_weights() * 0.05
+    d_codes, d_targets = torch.from_numpy(codes).cuda(), torch.from_numpy(targets).cuda()
+    lam0 = 9.5                                               # close to LAMBDA_MAX: accepted steps push it over 10 -> reset + dropout
+
+    a = cab.Network.from_weights(DEFAULT_DIMS, w0)
+    lam_a, st, trace = cab.train_epoch_dev(a, d_codes.data_ptr(), d_targets.data_ptr(), n, batch, lam0, dropout_seed=99, trace=True)
+    torch.cuda.synchronize()
+
+    b = cab.Network.from_weights(DEFAULT_DIMS, w0)
+    lam, accepted, resets, steps, hist = lam0, 0, 0, 0, []
+    for b0 in range(0, n, batch):
+        nb = min(batch, n - b0)
+        lam_c, acc, e0, e1 = C.c_double(lam), C.c_int(0), C.c_double(0), C.c_double(0)
+        cab._ck(cab.lib().cab_train_batch_dev(b._h, d_codes.data_ptr() + b0 * 64, d_targets.data_ptr() + b0 * 8, nb, C.byref(lam_c), 15.0, 1.1,
+                                              C.byref(acc), C.byref(e0), C.byref(e1), None))
+        lam = lam_c.value
+        accepted += acc.value
+        hist.append((e0.value, e1.value))
+        if lam < 1e-4 or lam > 10.0:                         # train.cpp:54-57
+            lam = 2.0
+            cab.Optimizer.dropout(b, 0.01, seed=99, offset=resets)
+            resets += 1
+        steps += 1
+    assert (st["steps"], st["accepted"], st["resets"]) == (steps, accepted, resets) and resets >= 1 and 0 < accepted
+    assert lam_a == lam
+    hist = np.array(hist)
+    assert np.abs(trace - hist).max() <= 1e-9 * np.abs(hist).max()          # fp64 sums in atomic order: rounding only
+    assert st["first_err"] == trace[0, 0] and st["last_err"] == trace[-1, 0]
+    assert np.abs(a.get_weights() - b.get_weights()).max() <= 1e-9
