@@ -18,7 +18,10 @@
  *   - weights travel as one flat fp64 array in n,i,j order — exactly line 3 of the network_dump text format
  *     (mcts_network/network.cpp:418-422).
  *   - *_host entry points take HOST pointers and include the H2D/D2H copies; *_dev take DEVICE pointers and a
- *     cudaStream_t (passed as void*) and are asynchronous.
+ *     cudaStream_t (passed as void*) and are asynchronous. A null stream means the legacy default stream for the fp64
+ *     evaluators (cab_eval_dev, cab_encode_dev); the tensor-core evaluators (cab_eval_bf16_dev, cab_eval_f16_dev,
+ *     cab_grad_bf16_dev) and the training entry points then run on the net's OWN non-blocking stream, which the
+ *     legacy default stream does not order against: pass a real stream when you time or chain them.
  *   - a cab_net is not thread-safe for mutation (train/dropout/set_weights); eval entry points may be called
  *     concurrently from many host threads on one net (mcts_network/tree.cpp:185 does exactly that). The fp64 and
  *     fused-fp16 evaluators then run concurrently (per-caller scratch); calls of the bf16 wide-net path

@@ -15,6 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "libmlp_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libchessai_ref.so")
+REF_SO_O0 = os.path.join(HERE, "_ref", "libchessai_ref_O0.so")   # the same translation units at the reference's as-shipped flags (no -O)
 
 _i8p = np.ctypeslib.ndpointer(dtype=np.int8, flags="C_CONTIGUOUS")
 _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
