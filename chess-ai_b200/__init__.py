@@ -534,7 +534,7 @@ class NetworkStorage:
 # ---- MCTS self-play resident on the GPU (csrc/cab_mcts.cu) ---------------------------------------------------------
 class MctsParams(C.Structure):
     _fields_ = [("games", C.c_int), ("roots", C.c_int), ("playouts_per_move", C.c_int), ("in_flight", C.c_int), ("max_moves", C.c_int),
-                ("network_priors", C.c_int), ("noise", C.c_int), ("reserved", C.c_int), ("save_ratio", C.c_double), ("seed", C.c_uint64)]
+                ("network_priors", C.c_int), ("noise", C.c_int), ("precision", C.c_int), ("save_ratio", C.c_double), ("seed", C.c_uint64)]
 
 
 class MctsStats(C.Structure):
@@ -548,9 +548,10 @@ class MctsStats(C.Structure):
 class SelfPlay:
     """tree::MCTS self-play with virtual-loss leaf batching, trees and rules on the device (tree.cpp, decider.cpp:31-61)."""
 
-    def __init__(self, net, games, playouts_per_move, roots=1, in_flight=8, max_moves=40, network_priors=0, noise=0, save_ratio=0.0, seed=1234):
+    def __init__(self, net, games, playouts_per_move, roots=1, in_flight=8, max_moves=40, network_priors=0, noise=0, save_ratio=0.0, seed=1234,
+                 precision=0):
         self.net = net
-        self.params = MctsParams(games, roots, playouts_per_move, in_flight, max_moves, network_priors, noise, 0, save_ratio, seed)
+        self.params = MctsParams(games, roots, playouts_per_move, in_flight, max_moves, network_priors, noise, precision, save_ratio, seed)
         self._h = _vp(None)
         _ck(lib().cab_mcts_create(net._h, C.byref(self.params), C.byref(self._h)))
 

@@ -789,7 +789,7 @@ int cab_mcts_create(cab_net *net, const cab_mcts_params *params, cab_mcts **out)
   *out = nullptr;
   const cab_mcts_params &p = *params;
   if (p.games <= 0 || p.roots <= 0 || p.roots > 64 || p.playouts_per_move <= 0 || p.in_flight <= 0 || p.in_flight > 4096 || p.max_moves < 0 ||
-      p.save_ratio < 0.0 || p.save_ratio > 1.0) { set_error("bad MCTS parameters"); return CAB_EINVAL; }
+      p.save_ratio < 0.0 || p.save_ratio > 1.0 || p.precision < 0 || p.precision > 1) { set_error("bad MCTS parameters"); return CAB_EINVAL; }
   if (!net->fp64_ok) { set_error("the network does not fit the fp64 evaluator"); return CAB_EINVAL; }
   CAB_CUDA(cudaSetDevice(net->device));
   cab_mcts *q = new cab_mcts();
@@ -866,7 +866,9 @@ int cab_mcts_run(cab_mcts *q, int search_only, long max_rounds, cab_mcts_stats *
     q->round_parity ^= 1;
     if (n_boards > 0) {
       CAB_CUDA(cudaEventRecord(q->ev0, q->stream));
-      const int rc = launch_forward(net, d.eval_codes[buf], n_boards, d.eval_out[buf], nullptr, 0, q->stream, nullptr, /*alone=*/true);
+      // precision 1: the fused fp16 tcgen05 evaluator (reduced precision: the search is then NOT the reference's, see the header)
+      const int rc = q->prm.precision == 1 ? cab_eval_f16_dev(net, d.eval_codes[buf], n_boards, d.eval_out[buf], q->stream)
+                                           : launch_forward(net, d.eval_codes[buf], n_boards, d.eval_out[buf], nullptr, 0, q->stream, nullptr, /*alone=*/true);
       if (rc != CAB_OK) return rc;
       CAB_CUDA(cudaEventRecord(q->ev1, q->stream));
       CAB_CUDA(cudaEventSynchronize(q->ev1));

@@ -66,6 +66,20 @@ static bool tc_supported(const cab_net *net) {
 }
 
 // ---- fused fp16 path for {64, N1, N2, N3, 1} nets (mlp_tc_fused.cuh) -------------------------------------------------
+// A leaf-queue flush in launches of a few thousand boards is bound by the HOST's launch rate (a 4 096-board launch of the
+// fused kernel runs ~5 us): cab_eval_f16_dev_batches captures its launch sequence once per (buffers, sizes, streams) into
+// a CUDA graph and replays it.
+constexpr int kGraphStreams = 8, kGraphCache = 8;
+struct BatchGraph {
+  const int8_t *codes = nullptr;
+  double *out = nullptr;
+  long n = 0, batch = 0;
+  int n_streams = 0;
+  cudaStream_t streams[kGraphStreams] = {};
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t last_used = 0;
+};
 struct F16State {
   uint8_t *image = nullptr;
   tcf::PackArgs pack{};
@@ -75,6 +89,10 @@ struct F16State {
   double *d_out = nullptr;
   long cap = 0;
   cudaStream_t stream = nullptr;
+  std::mutex graph_mu;
+  std::vector<BatchGraph> graphs;
+  uint64_t graph_clock = 0;
+  cudaEvent_t ev_fork = nullptr, ev_join[kGraphStreams] = {}, ev_done = nullptr;
 };
 
 static bool f16_supported(const cab_net *net) {
@@ -88,6 +106,13 @@ static void f16_delete(F16State *s) {
   if (!s) return;
   cudaFree(s->image); cudaFree(s->d_codes); cudaFree(s->d_out);
   if (s->stream) cudaStreamDestroy(s->stream);
+  for (auto &g : s->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_done) cudaEventDestroy(s->ev_done);
+  for (auto e : s->ev_join) if (e) cudaEventDestroy(e);
   delete s;
 }
 static void f16_free(cab_net *net) {
@@ -113,13 +138,14 @@ static int f16_construct(cab_net *net, F16State *s) {
   off += (uint32_t) s->pack.n_pad[2] * 4u;
   off = (off + 15u) & ~15u;
   s->args.image_bytes = off;
-  s->smem = (size_t) off + 1024 + 64 + tcf::kTile * sizeof(float);   // image, alignment slack, barriers, partial dot products
+  s->smem = (size_t) ((off + 1023u) & ~1023u) + 2 * tcf::kBoardBytes + 1024 + 512 + 2 * 3 * tcf::kTile * sizeof(float);   // image, two board buffers, alignment slack, barriers + flags, partial dot products
   if (s->smem > 227 * 1024) { set_error("the fp16 weight image (%u bytes) does not fit shared memory", off); return CAB_EINVAL; }
   CAB_CUDA(cudaMalloc(&s->image, off));
   s->pack.image = s->image;
   s->args.image = s->image;
   CAB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  CAB_CUDA(cudaFuncSetAttribute(tcf::mlp_tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem));
+  CAB_CUDA(cudaFuncSetAttribute(tcf::mlp_tc_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem));
+  CAB_CUDA(cudaFuncSetAttribute(tcf::mlp_tc_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s->smem));
   return CAB_OK;
 }
 
@@ -157,16 +183,57 @@ static int f16_prepare(cab_net *net, cudaStream_t stream) {
 }
 
 // the launch itself; the caller has run f16_prepare
-static int f16_launch(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream) {
+// max_ctas: the SMs this launch may count on (launches that run side by side on several streams share the device)
+static int f16_launch(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream, int max_ctas = 0) {
   F16State *s = static_cast<F16State *>(net->f16.load(std::memory_order_acquire));
   tcf::FusedArgs a = s->args;
   a.codes = d_codes;
   a.n_boards = n;
   a.out = d_out;
   const long tiles = (n + tcf::kTile - 1) / tcf::kTile;
-  tcf::mlp_tc_fused_kernel<<<(int) std::min<long>(tiles, net->sm_count), tcf::kThreads, s->smem, stream ? stream : s->stream>>>(a);
+  static const bool profile = getenv("CAB_F16_PROFILE") != nullptr;   // debug: clock stamps of every CTA's second tile, printed to stderr
+  long long *d_prof = nullptr;
+  if (profile) {
+    CAB_CUDA(cudaMalloc(&d_prof, (size_t) net->sm_count * 64 * sizeof(long long)));
+    CAB_CUDA(cudaMemset(d_prof, 0, (size_t) net->sm_count * 64 * sizeof(long long)));
+    a.prof = d_prof;
+  }
+  static const int ch = getenv("CAB_F16_CH") ? atoi(getenv("CAB_F16_CH")) : 16;   // accumulator columns per epilogue chunk (sweeps: 16 is best)
+  // every CTA fetches the whole weight image and its first tile runs without overlap: with fewer SMs to count on, fewer
+  // CTAs with more tiles each (equal shares)
+  const long cap = max_ctas > 0 ? std::min(max_ctas, net->sm_count) : net->sm_count;
+  const long tiles_per_cta = (tiles + cap - 1) / cap;
+  const int grid = (int) ((tiles + tiles_per_cta - 1) / tiles_per_cta);
+  cudaStream_t st = stream ? stream : s->stream;
+  if (ch == 32) tcf::mlp_tc_fused_kernel<32><<<grid, tcf::kThreadsP, s->smem, st>>>(a);
+  else tcf::mlp_tc_fused_kernel<16><<<grid, tcf::kThreadsP, s->smem, st>>>(a);
   net->launches++;
   CAB_CUDA(cudaGetLastError());
+  if (profile) {
+    CAB_CUDA(cudaDeviceSynchronize());
+    std::vector<long long> h((size_t) net->sm_count * 64);
+    CAB_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_prof);
+    double e[8] = {}, m[10] = {}, ws[16] = {}, we[16] = {};
+    int n_cta = 0;
+    for (int c = 0; c < grid; ++c) {
+      const long long *p = &h[(size_t) c * 64];
+      if (p[0] == 0 || p[7] == 0 || p[16] == 0) continue;
+      ++n_cta;
+      for (int i = 0; i < 8; ++i) e[i] += (double) (p[i] - p[0]);
+      for (int i = 0; i < 10; ++i) m[i] += (double) (p[16 + i] - p[0]);
+      for (int i = 0; i < 16; ++i) { ws[i] += (double) (p[48 + i] - p[0]); we[i] += (double) (p[32 + i] - p[0]); }
+    }
+    if (n_cta > 0) {
+      fprintf(stderr, "[f16 profile] boards=%ld ctas=%d  epilogue warp 0 (cycles after tile start): d0_full %.0f epi0_done %.0f d1_full %.0f epi1_done %.0f a0_stored %.0f d2_full %.0f final_done %.0f\n",
+              n, n_cta, e[1] / n_cta, e[2] / n_cta, e[3] / n_cta, e[4] / n_cta, e[5] / n_cta, e[6] / n_cta, e[7] / n_cta);
+      fprintf(stderr, "[f16 profile]   MMA thread: loop_top %.0f a0_seen %.0f L0_issued %.0f e0_first %.0f e0_last %.0f L1_committed %.0f e1_first %.0f e1_last %.0f L2_committed %.0f\n",
+              m[0] / n_cta, m[1] / n_cta, m[2] / n_cta, m[3] / n_cta, m[4] / n_cta, m[5] / n_cta, m[6] / n_cta, m[7] / n_cta, m[8] / n_cta);
+      fprintf(stderr, "[f16 profile]   MMA thread waited %.0f cycles on e_ready in the layer-2 loop; epilogue 1 start / end per warp:", (m[9] - m[0]) / n_cta);
+      for (int i = 0; i < 16; ++i) fprintf(stderr, " %.0f/%.0f", ws[i] / n_cta, we[i] / n_cta);
+      fprintf(stderr, "\n");
+    }
+  }
   return CAB_OK;
 }
 static int f16_forward(cab_net *net, const int8_t *d_codes, long n, double *d_out, cudaStream_t stream) {
@@ -456,12 +523,82 @@ int cab_eval_f16_dev(cab_net *net, const int8_t *codes_dev, long n, double *out_
   return f16_forward(net, codes_dev, n, out_dev, (cudaStream_t) stream);
 }
 
+// The launches of one cab_eval_f16_dev_batches call as a CUDA graph: captured on the caller's streams (fork from
+// streams[0], round-robin launches, join), cached by (buffers, sizes, streams), replayed on streams[0]; the other
+// streams then wait for the replay, so every caller stream still orders behind the whole call.
+static int f16_batches_graph(cab_net *net, F16State *s, const int8_t *codes_dev, long n, long batch, double *out_dev,
+                             void *const *streams, int n_streams) {
+  std::lock_guard<std::mutex> lk(s->graph_mu);
+  if (s->ev_fork == nullptr) {
+    CAB_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    CAB_CUDA(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
+    for (auto &e : s->ev_join) CAB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  BatchGraph *g = nullptr;
+  for (auto &c : s->graphs) {
+    bool same = c.codes == codes_dev && c.out == out_dev && c.n == n && c.batch == batch && c.n_streams == n_streams;
+    for (int i = 0; same && i < n_streams; ++i) same = c.streams[i] == (cudaStream_t) streams[i];
+    if (same) { g = &c; break; }
+  }
+  const long n_launches = (n + batch - 1) / batch;
+  if (g == nullptr) {
+    if ((int) s->graphs.size() >= kGraphCache) {            // evict the least recently used
+      size_t old = 0;
+      for (size_t i = 1; i < s->graphs.size(); ++i) if (s->graphs[i].last_used < s->graphs[old].last_used) old = i;
+      cudaGraphExecDestroy(s->graphs[old].exec);
+      cudaGraphDestroy(s->graphs[old].graph);
+      s->graphs.erase(s->graphs.begin() + old);
+    }
+    BatchGraph c;
+    c.codes = codes_dev; c.out = out_dev; c.n = n; c.batch = batch; c.n_streams = n_streams;
+    for (int i = 0; i < n_streams; ++i) c.streams[i] = (cudaStream_t) streams[i];
+    cudaStream_t s0 = c.streams[0];
+    CAB_CUDA(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
+    int rc = CAB_OK;
+    cudaError_t e = cudaEventRecord(s->ev_fork, s0);
+    for (int i = 1; e == cudaSuccess && i < n_streams; ++i) e = cudaStreamWaitEvent(c.streams[i], s->ev_fork, 0);
+    long k = 0;
+    const int share = std::max(1, net->sm_count / (int) std::min<long>(n_streams, n_launches));   // SMs per concurrent launch
+    for (long b0 = 0; e == cudaSuccess && rc == CAB_OK && b0 < n; b0 += batch, ++k)
+      rc = f16_launch(net, codes_dev + b0 * 64, std::min(batch, n - b0), out_dev + b0, c.streams[k % n_streams], share);
+    for (int i = 1; e == cudaSuccess && i < n_streams; ++i) {
+      e = cudaEventRecord(s->ev_join[i], c.streams[i]);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(s0, s->ev_join[i], 0);
+    }
+    const cudaError_t e_end = cudaStreamEndCapture(s0, &c.graph);
+    if (rc != CAB_OK) { if (c.graph) cudaGraphDestroy(c.graph); return rc; }
+    if (e != cudaSuccess || e_end != cudaSuccess) { if (c.graph) cudaGraphDestroy(c.graph); return cuda_fail(e != cudaSuccess ? e : e_end, "graph capture", __FILE__, __LINE__); }
+    net->launches -= n_launches;                             // f16_launch counted the captured launches; the replay below counts them
+    e = cudaGraphInstantiate(&c.exec, c.graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(c.graph); return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+    s->graphs.push_back(c);
+    g = &s->graphs.back();
+  }
+  g->last_used = ++s->graph_clock;
+  CAB_CUDA(cudaGraphLaunch(g->exec, g->streams[0]));
+  net->launches += n_launches;
+  if (n_streams > 1) {
+    CAB_CUDA(cudaEventRecord(s->ev_done, g->streams[0]));
+    for (int i = 1; i < n_streams; ++i) CAB_CUDA(cudaStreamWaitEvent(g->streams[i], s->ev_done, 0));
+  }
+  return CAB_OK;
+}
+
 int cab_eval_f16_dev_batches(cab_net *net, const int8_t *codes_dev, long n, long batch, double *out_dev, void *const *streams,
                              int n_streams) {
   if (!net || n < 0 || batch <= 0 || n_streams <= 0 || !streams || (n > 0 && (!codes_dev || !out_dev))) { set_error("bad argument"); return CAB_EINVAL; }
   CAB_CUDA(cudaSetDevice(net->device));
   int rc = f16_prepare(net, (cudaStream_t) streams[0]);     // weights packed (and that stream drained) before any launch
   if (rc != CAB_OK) return rc;
+  // many small launches: replay them as one graph (real streams only: the legacy default stream cannot be captured)
+  static const bool use_graph = getenv("CAB_F16_NO_GRAPH") == nullptr && getenv("CAB_F16_PROFILE") == nullptr;
+  bool real_streams = n_streams <= kGraphStreams;
+  for (int i = 0; real_streams && i < n_streams; ++i) real_streams = streams[i] != nullptr;
+  if (use_graph && real_streams && (n + batch - 1) / batch >= 8) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t) streams[0], &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone)
+      return f16_batches_graph(net, static_cast<F16State *>(net->f16.load(std::memory_order_acquire)), codes_dev, n, batch, out_dev, streams, n_streams);
+  }
   int i = 0;
   for (long b0 = 0; b0 < n; b0 += batch, ++i) {
     rc = f16_forward(net, codes_dev + b0 * 64, std::min(batch, n - b0), out_dev + b0, (cudaStream_t) streams[i % n_streams]);

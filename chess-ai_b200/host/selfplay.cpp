@@ -10,7 +10,7 @@
 // that keep the reference's own search, integration/batched_mcts.cpp.)
 //
 //   selfplay <latest.txt> <games> <playouts_per_move> <moves_per_game> <unused> <in_flight_per_tree> <network_priors>
-//            [device] [seed] [cases_path] [save_ratio] [precision: fp64] [roots] [noise]
+//            [device] [seed] [cases_path] [save_ratio] [precision: fp64 | f16] [roots] [noise]
 // (roots = independent trees per move, merged like the reference's root-parallel threads; each gets playouts / roots;
 //  cases_path "-" = none; noise 0 switches the root Dirichlet noise off: deterministic searches)
 // No CPU fallback: needs libchessai_b200.so and a GPU.
@@ -25,7 +25,7 @@
 int main(int argc, char **argv) {
   if (argc < 8) {
     std::fprintf(stderr, "usage: %s latest.txt games playouts_per_move moves_per_game - in_flight_per_tree network_priors "
-                         "[device] [seed] [cases_path] [save_ratio] [fp64] [roots] [noise]\n", argv[0]);
+                         "[device] [seed] [cases_path] [save_ratio] [fp64|f16] [roots] [noise]\n", argv[0]);
     return 2;
   }
   cab_mcts_params p;
@@ -39,10 +39,11 @@ int main(int argc, char **argv) {
   p.seed = argc > 9 ? std::strtoull(argv[9], nullptr, 10) : 1234;
   const char *cases_path = argc > 10 && std::strcmp(argv[10], "-") != 0 ? argv[10] : nullptr;
   p.save_ratio = cases_path ? (argc > 11 ? std::atof(argv[11]) : 0.1) : 0.0;
-  if (argc > 12 && std::strcmp(argv[12], "fp64") != 0) {
-    std::fprintf(stderr, "precision '%s': the device-resident search evaluates with the fp64 reference-precision kernel only\n", argv[12]);
+  if (argc > 12 && std::strcmp(argv[12], "fp64") != 0 && std::strcmp(argv[12], "f16") != 0) {
+    std::fprintf(stderr, "precision '%s': fp64 (the reference's search) or f16 (fused fp16 tcgen05 evaluator, reduced precision)\n", argv[12]);
     return 2;
   }
+  p.precision = argc > 12 && std::strcmp(argv[12], "f16") == 0 ? 1 : 0;
   p.roots = argc > 13 ? std::atoi(argv[13]) : 1;
   p.noise = argc > 14 ? std::atoi(argv[14]) != 0 : 1;
   if (p.roots < 1) p.roots = 1;

@@ -160,7 +160,7 @@ typedef struct cab_mcts_params {
   int max_moves;          /* a game stops after this many moves (or at mate / stalemate / 50 plies without capture) */
   int network_priors;     /* 0: decider.cpp:52-57 as shipped (constant logit 20 unless the opponent has no reply); 1: every child evaluated */
   int noise;              /* 1: Dirichlet(0.2) noise mixed 25 % into the root priors (tree.cpp:318-347), Philox-driven */
-  int reserved;
+  int precision;          /* 0: fp64 evaluator (the reference's search); 1: the fused fp16 tcgen05 evaluator (cab_eval_f16_*: faster, NOT a parity path) */
   double save_ratio;      /* probability of keeping the board after a move as a training case (initialization.cpp:221-227) */
   uint64_t seed;
 } cab_mcts_params;
