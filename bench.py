@@ -432,14 +432,14 @@ def main():
     # ---- configs[2]: MCTS self-play resident on the device, independent games per GPU (no collective) ------------------
     selfplay = None
     if not args.no_selfplay:
-        sp = cab.SelfPlay(net, games=512, playouts_per_move=800, roots=4, in_flight=16, max_moves=args.selfplay_moves, network_priors=1,
+        sp = cab.SelfPlay(net, games=512, playouts_per_move=800, roots=8, in_flight=16, max_moves=args.selfplay_moves, network_priors=1,
                           noise=1, save_ratio=0.1, seed=1234 + rank)
         barrier()
         st = sp.run()
         secs = max_over_ranks(st["seconds"])
         tot = {k: sum_over_ranks(st[k]) for k in ("playouts", "boards_evaluated", "moves_played", "expansions", "cases_kept")}
         selfplay = {"value": tot["playouts"] / secs, "unit": "playouts/s", "positions_evaluated_per_s": tot["boards_evaluated"] / secs,
-                    "games_per_gpu": 512, "playouts_per_move": 800, "moves_per_game": args.selfplay_moves, "roots": 4, "in_flight_per_tree": 16,
+                    "games_per_gpu": 512, "playouts_per_move": 800, "moves_per_game": args.selfplay_moves, "roots": 8, "in_flight_per_tree": 16,
                     "network_priors": 1, "noise": 1, "seconds": secs, "moves_played": tot["moves_played"], "expansions": tot["expansions"],
                     "cases_kept": tot["cases_kept"], "evaluator_busy_rank0": st["evaluator_seconds"] / st["seconds"],
                     "rounds_rank0": st["rounds"], "arena_full_rank0": st["arena_full"], "eval_full_rank0": st["eval_full"], "scaling": "weak",
@@ -447,6 +447,20 @@ def main():
                               "move generation, expansion, priors and game rules on the device (cab_mcts_run), fp64 evaluator",
                     "timing": "wall clock inside cab_mcts_run (it ends with a device synchronise), max over ranks"}
         sp.close()
+        # the same games with the fused fp16 tcgen05 evaluator behind the search (reduced precision: not the reference's search)
+        try:
+            sp = cab.SelfPlay(net, games=512, playouts_per_move=800, roots=8, in_flight=16, max_moves=args.selfplay_moves, network_priors=1,
+                              noise=1, save_ratio=0.1, seed=1234 + rank, precision=1)
+            barrier()
+            st = sp.run()
+            secs = max_over_ranks(st["seconds"])
+            selfplay["f16_evaluator"] = {"value": sum_over_ranks(st["playouts"]) / secs, "unit": "playouts/s",
+                                         "positions_evaluated_per_s": sum_over_ranks(st["boards_evaluated"]) / secs, "seconds": secs,
+                                         "evaluator_busy_rank0": st["evaluator_seconds"] / st["seconds"],
+                                         "note": "cab_mcts_params.precision = 1: priors and leaf values from cab_eval_f16_dev"}
+            sp.close()
+        except Exception as exc:
+            selfplay["f16_evaluator"] = {"error": str(exc)}
 
     if rank != 0:
         if world > 1:
