@@ -377,9 +377,25 @@ def main():
         torch.cuda.synchronize()
         gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
         targets = (targets + 0.05 * torch.randn(n_local, dtype=torch.float64, device="cuda", generator=gen)).clamp_(-4, 4)
-        student = cab.Network.randomNetwork(DEFAULT_DIMS, device=local_rank, seed=1234)   # same seed: identical replicas
-        student.set_weights(student.get_weights() * 0.1)
-        par = dpm.DataParallel(cab, student) if world > 1 else None
+        def new_student():
+            s_net = cab.Network.randomNetwork(DEFAULT_DIMS, device=local_rank, seed=1234)   # same seed: identical replicas
+            s_net.set_weights(s_net.get_weights() * 0.1)
+            return s_net
+        student = new_student()
+        # the collective of the data-parallel step: fused into the update kernel over NVLink peer memory (cab_dp_peer_*);
+        # NCCL all-reduces (cab_dp_init) if the ranks cannot map each other's memory, and as a second timing beside it
+        par, collective, nccl_note = None, "none", None
+        if world > 1:
+            mode = os.environ.get("CAB_BENCH_COLLECTIVE", "peer")
+            try:
+                par = dpm.DataParallel(cab, student, peer=(mode == "peer"))
+                collective = ("gradient sum over peer-mapped buffers fused into the update kernel + 8-byte peer stores for E' (no NCCL in the step)"
+                              if mode == "peer" else "ncclAllReduce(64220 fp64) + 1 scalar per step")
+            except Exception as exc:             # every rank fails alike (same box): fall back together
+                nccl_note = "peer mode unavailable (%s): NCCL" % exc
+                student = new_student()
+                par = dpm.DataParallel(cab, student)
+                collective = "ncclAllReduce(64220 fp64) + 1 scalar per step"
 
         def run_epoch(first, n, lam, seed):
             """n resident cases from `first` on as minibatches of B_TRAIN; device time of the whole call, max over ranks."""
@@ -413,7 +429,7 @@ def main():
                  "flop_per_sample": 8 * N_WEIGHTS, "flop_note": "8P per sample (fwd 2P + dX 2P + dW 2P + re-fwd 2P); the update is per step",
                  "tflops": 8 * N_WEIGHTS * world * B_TRAIN * t_steps / secs * 1e-12,
                  "gpu_launches": n_launch, "api": "cab_train_epoch_dev: decisions, rollback and reset+dropout on the device, one wait at the end",
-                 "collective": "ncclAllReduce(64220 fp64) + 1 scalar per step" if world > 1 else "none",
+                 "collective": collective, "collective_note": nccl_note,
                  "replicas_bit_identical": same, "weights_sha256": digest[:16], "scaling": "weak",
                  "timing": "CUDA events around the whole call on the launching stream, max over ranks"}
 
@@ -427,6 +443,18 @@ def main():
                     "config": "configs[3]: data-parallel training of the default MLP on 10 x 2^20 synthetic pairs, dropout rule active, lambda0 = 2.0"}
         if par is not None:
             par.shutdown()
+        if world > 1 and par is not None and par.peer:      # the same weak-scaling steps with NCCL all-reduces, for comparison
+            try:
+                student = new_student()
+                par = dpm.DataParallel(cab, student)
+                lam, _, _, _ = run_epoch(0, 16 * B_TRAIN, 0.5, 0x5EED)
+                lam, st, secs, _ = run_epoch(0, t_steps * B_TRAIN, lam, 0x5EED + 1)
+                same, _ = digest_check()
+                train["with_nccl_allreduce"] = {"value": world * B_TRAIN * t_steps / secs, "ms_per_step": secs / t_steps * 1e3,
+                                                "accepted_steps": st["accepted"], "replicas_bit_identical": same}
+                par.shutdown()
+            except Exception as exc:
+                train["with_nccl_allreduce"] = {"error": str(exc)}
         del targets, student
 
     # ---- configs[2]: MCTS self-play resident on the device, independent games per GPU (no collective) ------------------

@@ -89,6 +89,8 @@ _SIGS = {
     "cab_dp_unique_id": [_vp],
     "cab_dp_init": [_vp, _vp, C.c_int, C.c_int],
     "cab_dp_shutdown": [_vp],
+    "cab_dp_peer_export": [_vp, _vp],
+    "cab_dp_peer_attach": [_vp, _vp, C.c_int, C.c_int],
     "cab_grad_buffer": [_vp, C.POINTER(_vp), _lp],
     "cab_eval_f16_dev": [_vp, _vp, C.c_long, _vp, _vp],
     "cab_eval_f16_host": [_vp, _i8p, C.c_long, _f64p],

@@ -556,6 +556,7 @@ int cab_net_destroy(cab_net *net) {
     delete c;
   }
   free_plan(&net->fwd); free_plan(&net->bwd);
+  dp_peer_detach(net);   // d_grad points into the peer exchange block while attached
   cudaFree(net->d_w); cudaFree(net->d_dw); cudaFree(net->d_grad); cudaFree(net->d_acts); cudaFree(net->d_psis);
   cudaFree(net->d_tcodes); cudaFree(net->d_ttargets); cudaFree(net->d_tout); cudaFree(net->d_tout_tc); cudaFree(net->d_scalars); cudaFree(net->d_ctl);
   if (net->train_stream) cudaStreamDestroy(net->train_stream);

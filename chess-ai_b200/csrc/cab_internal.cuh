@@ -126,6 +126,14 @@ struct cab_net {
   // data parallel
   void *nccl_comm = nullptr;
   int dp_rank = 0, dp_world = 1;
+  // data parallel over NVLink peer memory (cab_dp_peer_*): every rank's exchange block (two gradient buffers, E' slots,
+  // epoch flags) is mapped into every other rank's address space through CUDA IPC
+  void *peer_block = nullptr;              // this rank's block
+  void *peer_map[16] = {};                 // rank r's block in THIS address space (peer_map[dp_rank] == peer_block)
+  void **d_peer_table = nullptr;           // the same table on the device
+  double *d_grad_own = nullptr;            // the private gradient buffer d_grad points to outside peer mode
+  unsigned long long peer_epoch = 0;       // steps taken in peer mode (the flags' values)
+  int peer_world = 0;                      // > 1: the trainer reduces over peer memory instead of NCCL
   // eval contexts
   std::mutex mu;
   std::vector<cab::EvalCtx *> ctxs;
@@ -136,6 +144,8 @@ namespace cab {
 
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+void dp_peer_detach(cab_net *net);   // cab_train.cu
 
 // cab_api.cu, used by the other translation units
 int ensure_packed(cab_net *net, cudaStream_t stream, bool drain);

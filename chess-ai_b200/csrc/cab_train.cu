@@ -313,6 +313,25 @@ static int ensure_tout(cab_net *net, long n) {   // bf16 mode: only the output b
   return CAB_OK;
 }
 
+// layout of a rank's exchange block (train_kernels.cuh: peer kernels)
+static size_t peer_block_bytes(long nw, size_t *off_grad, size_t *off_e1, size_t *off_fg, size_t *off_fe) {
+  const size_t g = (size_t) (nw + 4) * sizeof(double);
+  off_grad[0] = 0; off_grad[1] = (g + 255) / 256 * 256;
+  *off_e1 = off_grad[1] + (g + 255) / 256 * 256;
+  *off_fg = *off_e1 + 2 * kPeerMax * sizeof(double);
+  *off_fe = *off_fg + kPeerMax * sizeof(unsigned long long);
+  return *off_fe + kPeerMax * sizeof(unsigned long long);
+}
+static PeerArgs peer_args(const cab_net *net, unsigned long long epoch) {
+  PeerArgs a{};
+  a.table = net->d_peer_table;
+  a.rank = net->dp_rank; a.world = net->peer_world;
+  a.epoch = epoch;
+  a.nw = net->n_weights;
+  peer_block_bytes(net->n_weights, a.off_grad, &a.off_e1, &a.off_flags_grad, &a.off_flags_e1);
+  return a;
+}
+
 // One minibatch step, ENQUEUED on `stream` and left there: forward with saved activations, backward, gradient,
 // (all-reduce), update with the device-resident lambda, re-forward, E', (all-reduce), decision + rollback + reset rule
 // on the device (decide_kernel ...). Nothing here waits for the GPU: consecutive steps queue up behind each other.
@@ -324,6 +343,12 @@ static int enqueue_step(cab_net *net, const int8_t *d_codes, const double *d_tar
   TrainCtl *ctl = static_cast<TrainCtl *>(net->d_ctl);
   const long nw = net->n_weights;
   const int ew_grid = (int) std::min<long>((nw + 255) / 256, 148L * 8);
+  const bool peer = net->peer_world > 1;
+  PeerArgs pa{};
+  if (peer) {   // this step's gradient buffer inside the exchange block (parity of the epoch)
+    pa = peer_args(net, ++net->peer_epoch);
+    net->d_grad = reinterpret_cast<double *>(static_cast<char *>(net->peer_block) + pa.off_grad[pa.epoch & 1]);
+  }
   net->pack_dirty = net->tc_dirty = net->f16_dirty = true;     // the previous step may have rolled back or diluted the weights
   if (!bf16) {
     std::lock_guard<std::mutex> lk(net->mu);
@@ -342,11 +367,19 @@ static int enqueue_step(cab_net *net, const int8_t *d_codes, const double *d_tar
     if (rc != CAB_OK) return rc;
     if ((rc = launch_grad(net, n, stream)) != CAB_OK) return rc;
   }
-  if (net->nccl_comm != nullptr) {  // sum of (G, E, -, count) over ranks
-    int nrc = g_nccl.AllReduce(net->d_grad, net->d_grad, (size_t) nw + 4, kNcclDouble, kNcclSum, net->nccl_comm, stream);
-    if (nrc != 0) return nccl_fail(nrc, "ncclAllReduce(grad)");
+  const double *d_tail = net->d_grad + nw;      // (sum E, -, count) of the whole batch, for the decision
+  if (peer) {   // all-reduce and update in one kernel over the ranks' mapped gradient buffers
+    peer_signal_kernel<<<1, 32, 0, stream>>>(pa);
+    peer_reduce_update_kernel<<<net->sm_count, 256, 0, stream>>>(pa, net->d_w, net->d_dw, ctl, net->d_scalars + 24);
+    d_tail = net->d_scalars + 24;
+    net->launches += 1;
+  } else {
+    if (net->nccl_comm != nullptr) {  // sum of (G, E, -, count) over ranks
+      int nrc = g_nccl.AllReduce(net->d_grad, net->d_grad, (size_t) nw + 4, kNcclDouble, kNcclSum, net->nccl_comm, stream);
+      if (nrc != 0) return nccl_fail(nrc, "ncclAllReduce(grad)");
+    }
+    apply_update_ctl_kernel<<<ew_grid, 256, 0, stream>>>(net->d_w, net->d_dw, net->d_grad, nw, ctl);
   }
-  apply_update_ctl_kernel<<<ew_grid, 256, 0, stream>>>(net->d_w, net->d_dw, net->d_grad, nw, ctl);
   net->launches += 2;
   net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   // re-forward (network.cpp:265) and E'
@@ -364,11 +397,15 @@ static int enqueue_step(cab_net *net, const int8_t *d_codes, const double *d_tar
   }
   CAB_CUDA(cudaMemsetAsync(net->d_scalars, 0, 2 * sizeof(double), stream));
   batch_error_kernel<<<(int) std::min<long>((n + 255) / 256, 148L * 4), 256, 0, stream>>>(d_tout, d_targets, n, net->d_scalars);
-  if (net->nccl_comm != nullptr) {
-    int nrc = g_nccl.AllReduce(net->d_scalars, net->d_scalars, 1, kNcclDouble, kNcclSum, net->nccl_comm, stream);
-    if (nrc != 0) return nccl_fail(nrc, "ncclAllReduce(E')");
+  if (peer) {
+    peer_decide_kernel<<<1, 32, 0, stream>>>(pa, ctl, d_tail, net->d_scalars, d_e_trace);                   // E' over the ranks + the decision
+  } else {
+    if (net->nccl_comm != nullptr) {
+      int nrc = g_nccl.AllReduce(net->d_scalars, net->d_scalars, 1, kNcclDouble, kNcclSum, net->nccl_comm, stream);
+      if (nrc != 0) return nccl_fail(nrc, "ncclAllReduce(E')");
+    }
+    decide_kernel<<<1, 1, 0, stream>>>(ctl, d_tail, net->d_scalars, d_e_trace);                             // network.cpp:269-273, train.cpp:54-57
   }
-  decide_kernel<<<1, 1, 0, stream>>>(ctl, net->d_grad + nw, net->d_scalars, d_e_trace);                     // network.cpp:269-273, train.cpp:54-57
   rollback_ctl_kernel<<<ew_grid, 256, 0, stream>>>(net->d_w, net->d_dw, nw, ctl);                           // :274-277 when rejected
   dropout_ctl_kernel<<<ew_grid, 256, 0, stream>>>(net->d_w, nw, 0.01, ctl);                                 // only behind a lambda reset
   net->launches += 4;
@@ -404,6 +441,7 @@ static int train_batch_impl(cab_net *net, const int8_t *d_codes, const double *d
   CAB_CUDA(cudaMemcpyAsync(&h, net->d_ctl, sizeof h, cudaMemcpyDeviceToHost, stream));
   if (bf16 && (rc = tc_turn_end(net, stream)) != CAB_OK) return rc;
   CAB_CUDA(cudaStreamSynchronize(stream));
+  if (h.peer_error) { set_error("data-parallel step: a peer's flag did not arrive (peer-memory mode)"); return CAB_ESTATE; }
   *lambda = h.lambda;
   if (accepted) *accepted = h.ok;
   if (err) *err = h.e0;
@@ -438,6 +476,7 @@ static int train_epoch_impl(cab_net *net, const int8_t *d_codes, const double *d
   if (e_trace_host != nullptr) CAB_CUDA(cudaMemcpyAsync(e_trace_host, trace.p, (size_t) steps * 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
   if (bf16 && (rc = tc_turn_end(net, stream)) != CAB_OK) return rc;
   CAB_CUDA(cudaStreamSynchronize(stream));
+  if (h.peer_error) { set_error("data-parallel epoch: a peer's flag did not arrive (peer-memory mode)"); return CAB_ESTATE; }
   *lambda = h.lambda;
   if (stats) {
     stats->steps = (long) h.steps; stats->accepted = (long) h.accepted; stats->resets = h.resets;
@@ -501,11 +540,74 @@ static int train_sequence_impl(cab_net *net, const int8_t *codes, const double *
   return CAB_OK;
 }
 
+// leaves peer mode: closes the peers' mappings, frees the exchange block, d_grad back to the private buffer
+void dp_peer_detach(cab_net *net) {
+  if (net->peer_block == nullptr) return;
+  cudaSetDevice(net->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < net->peer_world; ++r)
+    if (r != net->dp_rank && net->peer_map[r] != nullptr) cudaIpcCloseMemHandle(net->peer_map[r]);
+  cudaFree(net->peer_block);
+  cudaFree(net->d_peer_table);
+  net->peer_block = nullptr;
+  net->d_peer_table = nullptr;
+  for (auto &m : net->peer_map) m = nullptr;
+  net->d_grad = net->d_grad_own;
+  net->peer_world = 0;
+  net->peer_epoch = 0;
+}
+
 }  // namespace cab
 
 using namespace cab;
 
 extern "C" {
+
+int cab_dp_peer_export(cab_net *net, void *handle64_out) {
+  if (!net || !handle64_out) { set_error("null argument"); return CAB_EINVAL; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries the IPC handle as 64 bytes");
+  CAB_CUDA(cudaSetDevice(net->device));
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  if (net->peer_block == nullptr) {
+    size_t og[2], oe, ofg, ofe;
+    const size_t bytes = peer_block_bytes(net->n_weights, og, &oe, &ofg, &ofe);
+    CAB_CUDA(cudaMalloc(&net->peer_block, bytes));
+    CAB_CUDA(cudaMemset(net->peer_block, 0, bytes));
+    CAB_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  CAB_CUDA(cudaIpcGetMemHandle(&h, net->peer_block));
+  memcpy(handle64_out, &h, 64);
+  return CAB_OK;
+}
+
+int cab_dp_peer_attach(cab_net *net, const void *handles64, int rank, int world) {
+  if (!net || !handles64 || world < 2 || world > kPeerMax || rank < 0 || rank >= world) { set_error("bad argument (2 <= world <= %d)", kPeerMax); return CAB_EINVAL; }
+  if (net->peer_block == nullptr) { set_error("cab_dp_peer_export first"); return CAB_ESTATE; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { net->peer_map[r] = net->peer_block; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char *>(handles64) + 64 * r, 64);
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; ++q)
+        if (q != rank && net->peer_map[q]) { cudaIpcCloseMemHandle(net->peer_map[q]); net->peer_map[q] = nullptr; }
+      return cuda_fail(e, "cudaIpcOpenMemHandle (peer access between the ranks' devices is required)", __FILE__, __LINE__);
+    }
+    net->peer_map[r] = p;
+  }
+  CAB_CUDA(cudaMalloc(&net->d_peer_table, kPeerMax * sizeof(void *)));
+  CAB_CUDA(cudaMemcpy(net->d_peer_table, net->peer_map, kPeerMax * sizeof(void *), cudaMemcpyHostToDevice));
+  net->d_grad_own = net->d_grad;
+  net->dp_rank = rank;
+  net->dp_world = world;
+  net->peer_world = world;
+  net->peer_epoch = 0;
+  return CAB_OK;
+}
 
 int cab_dropout(cab_net *net, double rate, uint64_t seed, uint64_t offset, long *hits) {
   if (!net) { set_error("null argument"); return CAB_EINVAL; }
@@ -659,6 +761,7 @@ int cab_dp_init(cab_net *net, const void *id128, int rank, int world) {
 int cab_dp_shutdown(cab_net *net) {
   if (!net) return CAB_OK;
   drop_grad_plan(net);
+  dp_peer_detach(net);
   if (net->nccl_comm != nullptr && g_nccl.CommDestroy) {
     g_nccl.CommDestroy(net->nccl_comm);
     net->nccl_comm = nullptr;

@@ -453,6 +453,7 @@ struct TrainCtl {              // device-resident state of the minibatch trainer
   int resets;
   long long accepted, steps;
   unsigned long long seed;     // Philox key of the dropout
+  int peer_error;              // a peer's flag did not arrive in time (cab_dp_peer_*): the results are not valid
 };
 // dW = (lambda / count) * G ; W += dW with lambda read on the device
 __global__ void __launch_bounds__(256) apply_update_ctl_kernel(double *__restrict__ w, double *__restrict__ dw, const double *__restrict__ grad,
@@ -466,9 +467,8 @@ __global__ void __launch_bounds__(256) apply_update_ctl_kernel(double *__restric
 }
 // E' < E ? accept (lambda *= rate while lambda < max_const) : reject (lambda /= rate; the rollback kernel undoes the update)
 // (network.cpp:269-278), then the train loop's reset rule (train.cpp:54-57). grad_tail = {sum E, -, count}; e1_sum = sum E'.
-__global__ void decide_kernel(TrainCtl *ctl, const double *grad_tail, const double *e1_sum, double *e_trace) {
-  const double count = grad_tail[2];
-  const double e0 = grad_tail[0] / count, e1 = *e1_sum / count;
+__device__ __forceinline__ void decide_body(TrainCtl *ctl, double e0_sum, double count, double e1_sum, double *e_trace) {
+  const double e0 = e0_sum / count, e1 = e1_sum / count;
   const bool ok = e1 < e0;
   double lam = ctl->lambda;
   if (ok) { if (lam < ctl->max_const) lam *= ctl->rate; }
@@ -486,6 +486,110 @@ __global__ void decide_kernel(TrainCtl *ctl, const double *grad_tail, const doub
   ctl->ok = ok ? 1 : 0;
   ctl->accepted += ok ? 1 : 0;
   ctl->steps += 1;
+}
+__global__ void decide_kernel(TrainCtl *ctl, const double *grad_tail, const double *e1_sum, double *e_trace) {
+  decide_body(ctl, grad_tail[0], grad_tail[2], *e1_sum, e_trace);
+}
+
+// ---- data-parallel step over NVLink peer memory: the collective fused into the update --------------------------------
+// Every rank owns an exchange block {grad[2][nw + 4], e1[2][kPeerMax], flags_grad[kPeerMax], flags_e1[kPeerMax]} that
+// all ranks have mapped (CUDA IPC). Step e (epoch, from 1) uses the buffers of parity e & 1:
+//   peer_signal_kernel         after the gradient kernel: "my grad[e & 1] is complete" = e into flags_grad[me] of every rank
+//   peer_reduce_update_kernel  waits for all ranks' flags, then every rank sums the ranks' gradients itself, element by
+//                              element IN RANK ORDER (identical bits on every rank), and applies dW = (lambda / count) sum:
+//                              the all-reduce and apply_update_ctl_kernel in one pass over the weights, remote reads only
+//   peer_decide_kernel         E' the same way: 8 bytes stored into every rank's e1[e & 1][me] + flag, then decide_kernel
+// A buffer of parity p is rewritten two steps later; by then every rank has passed the next step's flag wait, which each
+// rank only signals after it has finished reading (stream order): one flag per step and buffer suffices.
+// Waits give up after ~2 s (a dead peer must not hang the GPU): TrainCtl::peer_error, reported by the host.
+constexpr int kPeerMax = 16;
+struct PeerArgs {
+  void *const *table;                        // [world] every rank's exchange block in this rank's address space
+  int rank, world;
+  unsigned long long epoch;
+  size_t off_grad[2], off_e1, off_flags_grad, off_flags_e1;
+  long nw;
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_peer_f64(const double *p) {   // never from a stale L1 line
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// lanes r < world of the calling warp wait until flags[r] >= epoch; false (warp-uniform) on timeout
+__device__ __forceinline__ bool peer_wait(const unsigned long long *flags, int world, unsigned long long epoch) {
+  const int r = threadIdx.x & 31;
+  bool ok = true;
+  if (r < world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flags + r) < epoch)
+      if (clock64() - t0 > 4000000000ll) { ok = false; break; }
+  }
+  return __all_sync(0xffffffffu, ok);
+}
+__global__ void peer_signal_kernel(const PeerArgs a) {             // <<<1, 32>>>
+  __threadfence_system();                                           // the gradient kernel's results, system-wide, before the flag
+  const int r = threadIdx.x;
+  if (r < a.world)
+    st_release_sys(reinterpret_cast<unsigned long long *>(static_cast<char *>(a.table[r]) + a.off_flags_grad) + a.rank, a.epoch);
+}
+__global__ void __launch_bounds__(256) peer_reduce_update_kernel(const PeerArgs a, double *__restrict__ w, double *__restrict__ dw, TrainCtl *ctl,
+                                                                  double *__restrict__ tail_out) {
+  __shared__ int s_ok;
+  __shared__ double s_tail[4];
+  const int p = (int) (a.epoch & 1);
+  if (threadIdx.x < 32) {
+    const bool ok = peer_wait(reinterpret_cast<const unsigned long long *>(static_cast<const char *>(a.table[a.rank]) + a.off_flags_grad), a.world, a.epoch);
+    if (threadIdx.x == 0) s_ok = ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_ok) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->peer_error = 1;
+    return;
+  }
+  if (threadIdx.x < 4) {                      // sum E, -, count, spare over the ranks
+    double t = 0.0;
+    for (int r = 0; r < a.world; ++r) t += ld_peer_f64(reinterpret_cast<const double *>(static_cast<const char *>(a.table[r]) + a.off_grad[p]) + a.nw + threadIdx.x);
+    s_tail[threadIdx.x] = t;
+    if (blockIdx.x == 0) tail_out[threadIdx.x] = t;
+  }
+  __syncthreads();
+  const double scale = ctl->lambda / s_tail[2];
+  const double *g[kPeerMax];
+#pragma unroll
+  for (int r = 0; r < kPeerMax; ++r) g[r] = r < a.world ? reinterpret_cast<const double *>(static_cast<const char *>(a.table[r]) + a.off_grad[p]) : nullptr;
+  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < a.nw; i += (long) gridDim.x * blockDim.x) {
+    double sum = 0.0;
+#pragma unroll
+    for (int r = 0; r < kPeerMax; ++r)
+      if (r < a.world) sum += ld_peer_f64(g[r] + i);
+    const double d = sum * scale;
+    dw[i] = d;
+    w[i] += d;
+  }
+}
+__global__ void peer_decide_kernel(const PeerArgs a, TrainCtl *ctl, const double *tail, const double *e1_local, double *e_trace) {   // <<<1, 32>>>
+  const int r = threadIdx.x, p = (int) (a.epoch & 1);
+  if (r < a.world) {
+    double *slot = reinterpret_cast<double *>(static_cast<char *>(a.table[r]) + a.off_e1) + p * kPeerMax + a.rank;
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(slot), "d"(*e1_local) : "memory");
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned long long *>(static_cast<char *>(a.table[r]) + a.off_flags_e1) + a.rank, a.epoch);
+  }
+  const char *mine = static_cast<const char *>(a.table[a.rank]);
+  const bool ok = peer_wait(reinterpret_cast<const unsigned long long *>(mine + a.off_flags_e1), a.world, a.epoch);
+  if (threadIdx.x != 0) return;
+  if (!ok || ctl->peer_error) { ctl->peer_error = 1; return; }
+  double e1 = 0.0;
+  for (int q = 0; q < a.world; ++q) e1 += ld_peer_f64(reinterpret_cast<const double *>(mine + a.off_e1) + p * kPeerMax + q);
+  decide_body(ctl, tail[0], tail[2], e1, e_trace);
 }
 __global__ void __launch_bounds__(256) rollback_ctl_kernel(double *__restrict__ w, const double *__restrict__ dw, long n,
                                                             const TrainCtl *__restrict__ ctl) {

@@ -30,11 +30,22 @@ def broadcast_bytes(payload, src=0):
 class DataParallel:
     """Wraps a Network for data-parallel minibatch training on the current torch.distributed world."""
 
-    def __init__(self, cab, network):
+    def __init__(self, cab, network, peer=False):
+        """peer=False: gradient all-reduce by NCCL inside the library. peer=True: the ranks' gradient buffers are mapped
+        into each other (CUDA IPC over NVLink peer access) and the reduction is fused into the update kernel."""
         import torch.distributed as dist
-        self.cab, self.net = cab, network
+        self.cab, self.net, self.peer = cab, network, peer
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         lib = cab.lib()
+        if peer:
+            mine = (C.c_ubyte * 64)()
+            cab._ck(lib.cab_dp_peer_export(network._h, mine))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine))
+            buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
+            cab._ck(lib.cab_dp_peer_attach(network._h, buf, self.rank, self.world))
+            dist.barrier()                      # nobody steps before every rank has mapped every block
+            return
         ident = (C.c_ubyte * 128)()
         if self.rank == 0:
             cab._ck(lib.cab_dp_unique_id(ident))
@@ -53,4 +64,9 @@ class DataParallel:
         return lam_c.value, bool(acc.value), e0.value, e1.value
 
     def shutdown(self):
+        if self.peer:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.synchronize()
+            dist.barrier()                      # nobody unmaps a block a peer may still read
         self.cab._ck(self.cab.lib().cab_dp_shutdown(self.net._h))

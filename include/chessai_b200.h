@@ -261,6 +261,15 @@ CAB_API int cab_dropout(cab_net *net, double rate, uint64_t seed, uint64_t offse
 CAB_API int cab_dp_unique_id(void *id128_out);                                   /* rank 0: ncclGetUniqueId (128 bytes) */
 CAB_API int cab_dp_init(cab_net *net, const void *id128, int rank, int world);   /* ncclCommInitRank on the net's device */
 CAB_API int cab_dp_shutdown(cab_net *net);
+/* The same data-parallel step WITHOUT a library collective on its critical path: every rank's gradient buffer is mapped
+ * into every other rank's address space (CUDA IPC; the ranks' devices must have peer access: NVLink / NVSwitch) and ONE
+ * kernel per step waits for the ranks' flags, sums the ranks' gradients in rank order (identical bits everywhere) and
+ * applies the update; E' crosses as 8-byte peer stores inside the decision kernel. One process per GPU:
+ *   every rank: cab_dp_peer_export -> exchange the 64-byte handles (any transport) -> cab_dp_peer_attach(all, rank, world)
+ * then cab_train_batch_* / cab_train_epoch_* as usual; cab_dp_shutdown detaches (after a barrier of the caller's).
+ * A peer that never signals makes the step return CAB_ESTATE after ~2 s instead of hanging. 2 <= world <= 16. */
+CAB_API int cab_dp_peer_export(cab_net *net, void *handle64_out);
+CAB_API int cab_dp_peer_attach(cab_net *net, const void *handles64, int rank, int world);
 /* raw device pointers of the gradient / scalar buffers, for callers that run their own collective
  * (e.g. torch.distributed): grad has n_weights doubles followed by 2 doubles (sum E, sum E') and 1 count. */
 CAB_API int cab_grad_buffer(cab_net *net, double **grad_dev, long *n_doubles);

@@ -52,6 +52,26 @@ def test_nccl_world2_training_matches_single_gpu(cab, tmp_path):
 
 
 @pytest.mark.gpu
+def test_peer_memory_world2_training_matches_single_gpu(cab, tmp_path):
+    """cab_dp_peer_*: the reduction over NVLink peer memory fused into the update kernel (no NCCL in the step)."""
+    if cab.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = run_workers("peer", str(tmp_path / "peer"), 29544)
+    assert r[0]["w_sha"] == r[1]["w_sha"] and r[0]["trace"] == r[1]["trace"]      # identical bits and decisions on both ranks
+    for (lam, acc, e0, e1), (lam_s, acc_s, e0_s, e1_s) in zip(r[0]["trace"], r[0]["trace_single"]):
+        assert (lam, acc) == (lam_s, acc_s)
+        assert abs(e0 - e0_s) <= 1e-10 * abs(e0_s) and abs(e1 - e1_s) <= 1e-8 * abs(e1_s)
+    assert r[0]["max_abs_w_diff_vs_single"] < 1e-10
+    # an epoch of resident minibatches (7 steps, the last one short), decisions on the device
+    assert r[0]["w_sha_epoch"] == r[1]["w_sha_epoch"] and r[0]["epoch"] == r[1]["epoch"]
+    ep, ep1 = r[0]["epoch"], r[0]["epoch_single"]
+    assert ep["stats"]["steps"] == ep1["stats"]["steps"] == 7 and ep["stats"]["accepted"] == ep1["stats"]["accepted"]
+    assert ep["lam"] == ep1["lam"]
+    assert np.allclose(np.array(ep["trace"]), np.array(ep1["trace"]), rtol=1e-8, atol=0)
+    assert r[0]["epoch_max_abs_w_diff_vs_single"] < 1e-10
+
+
+@pytest.mark.gpu
 def test_cpp_trainer_data_parallel_world2_matches_replicas(cab, tmp_path):
     """chess-ai_b200/lib/train in data-parallel mode: two processes, two GPUs, file rendezvous of the NCCL id;
     steps are accepted, only rank 0 reports and writes the checkpoint."""
