@@ -43,8 +43,16 @@ class DataParallel:
             handles = [None] * self.world
             dist.all_gather_object(handles, bytes(mine))
             buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
-            cab._ck(lib.cab_dp_peer_attach(network._h, buf, self.rank, self.world))
-            dist.barrier()                      # nobody steps before every rank has mapped every block
+            err = None
+            try:
+                cab._ck(lib.cab_dp_peer_attach(network._h, buf, self.rank, self.world))
+            except Exception as exc:            # e.g. no peer access between two of the devices
+                err = str(exc)
+            errs = [None] * self.world          # all ranks agree on the outcome (this is also the barrier: nobody steps
+            dist.all_gather_object(errs, err)   # before every rank has mapped every block)
+            if any(e is not None for e in errs):
+                lib.cab_dp_shutdown(network._h)
+                raise RuntimeError("peer-memory data parallel unavailable: %s" % next(e for e in errs if e is not None))
             return
         ident = (C.c_ubyte * 128)()
         if self.rank == 0:
