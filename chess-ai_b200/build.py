@@ -68,7 +68,7 @@ def build(verbose=False, force=False):
     if force or _stale(fb, [fb_src, LIB]):
         subprocess.check_call([gxx, "-std=c++17", "-O2", "-static-libstdc++", "-static-libgcc", "-I/usr/local/cuda/include", "-o", fb, fb_src,
                                "-L" + LIB_DIR, "-lchessai_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN"])
-    for name in ("pipe_peaks", "tma_stream"):      # microbenchmarks behind the roofline denominators / design choices
+    for name in ("pipe_peaks", "tma_stream", "act_bench", "mufu_bench", "tmem_bench", "mma_bench"):   # microbenchmarks behind the roofline denominators / design choices
         tool = os.path.join(LIB_DIR, name)
         tsrc = os.path.join(CSRC, "tools", name + ".cu")
         if force or _stale(tool, [tsrc]):

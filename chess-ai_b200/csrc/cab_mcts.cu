@@ -648,6 +648,14 @@ __global__ void __launch_bounds__(128) mcts_game_kernel(const Dev d) {
   }
 }
 
+// a new cab_mcts_run: the "searched, waiting to be read" marks of a previous search-only call fall (the finished trees are
+// either re-marked at once, search-only again, or their move is played)
+__global__ void __launch_bounds__(128) mcts_clear_search_kernel(const Dev d) {
+  const int g = (int) (blockIdx.x * blockDim.x + threadIdx.x);
+  if (g == 0) d.cnt->searches_done = 0ull;
+  if (g < d.n_games) d.games[g].search_done = 0;
+}
+
 __global__ void __launch_bounds__(128) mcts_reset_kernel(const Dev d) {
   const int g = (int) (blockIdx.x * blockDim.x + threadIdx.x);
   if (g >= d.n_games) return;
@@ -847,7 +855,9 @@ int cab_mcts_run(cab_mcts *q, int search_only, long max_rounds, cab_mcts_stats *
   const int n_trees = d.n_games * d.roots;
   const auto t0 = std::chrono::steady_clock::now();
   Counters h{};
-  long rounds = 0;
+  long rounds = 0, idle_rounds = 0;
+  unsigned long long last_playouts = ~0ull, last_moves = ~0ull;
+  mcts_clear_search_kernel<<<(d.n_games + 127) / 128, 128, 0, q->stream>>>(d);
   for (;;) {
     const int buf = q->round_parity;
     mcts_game_kernel<<<(d.n_games + 127) / 128, 128, 0, q->stream>>>(d);
@@ -879,6 +889,10 @@ int cab_mcts_run(cab_mcts *q, int search_only, long max_rounds, cab_mcts_stats *
     const unsigned long long done = search_only ? h.searches_done : h.games_finished;
     if (done >= (unsigned long long) d.n_games && n_boards == 0) break;
     if (max_rounds > 0 && rounds >= max_rounds) break;
+    // a round that neither evaluates, nor completes a playout, nor plays a move cannot be followed by one that does
+    idle_rounds = (n_boards == 0 && h.playouts == last_playouts && h.moves == last_moves) ? idle_rounds + 1 : 0;
+    last_playouts = h.playouts; last_moves = h.moves;
+    if (idle_rounds >= 16) { set_error("MCTS: %ld rounds without progress (%llu of %d games done)", idle_rounds, done, d.n_games); return CAB_ESTATE; }
   }
   q->rounds += rounds;
   q->wall_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

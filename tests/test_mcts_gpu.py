@@ -129,3 +129,20 @@ def test_self_play_games_are_legal_and_yield_cases(cab, net):
     assert len(codes) == st["cases_kept"] and 100 < len(codes) < 48 * 10
     assert (np.abs(targets) <= 10.0 + 1e-12).all() and np.abs(targets).max() > 0
     sp.close()
+
+
+def test_self_play_with_the_fp16_evaluator_keeps_the_search_invariants(cab, net):
+    """cab_mcts_params.precision = 1: the fused fp16 tcgen05 evaluator behind the same search (no value parity claimed):
+    the tree bookkeeping must still hold and the games must finish."""
+    sp = cab.SelfPlay(net, games=32, playouts_per_move=64, roots=2, in_flight=8, max_moves=3, network_priors=1, noise=0, seed=5, precision=1)
+    st = sp.run(search_only=True)
+    assert st["searches_done"] == 32 and st["arena_full"] == 0 and st["eval_full"] == 0
+    for gidx in range(32):
+        rc = sp.root_children(gidx)
+        assert rc["root_visits"] == 64 and rc["visits"].sum() == 64 and len(rc["from"]) == 20     # the start position's 20 moves
+        assert abs(rc["prior"].sum() - 1.0) < 1e-12 and (rc["prior"] > 0).all()
+    st = sp.run()
+    assert st["games_finished"] == 32 and st["moves_played"] == 96
+    sp.close()
+    with pytest.raises(cab.CabError):
+        cab.SelfPlay(net, games=1, playouts_per_move=8, precision=7)

@@ -236,3 +236,28 @@ def test_bf16_ranking_picks_the_fp64_move_on_a_wide_net(cab):
         refined += got[4]
         total += got[3]
     assert refined < total
+
+
+def test_fused_f16_batches_replayed_as_a_graph_equal_one_launch(cab, golden):
+    """cab_eval_f16_dev_batches captures its launches once per (buffers, sizes, streams) and replays the graph: the
+    results equal one launch over all boards, the replay follows weight changes, other argument sets get their own graph."""
+    import torch
+    dims = [64, 144, 225, 100, 1]
+    net = cab.Network.from_weights(dims, scaled_weights(dims, 4))
+    n = 40 * 1024 + 77
+    codes = torch.from_numpy(np.ascontiguousarray(np.tile(golden["syn_codes"], (21, 1))[:n])).cuda()
+    out, ref = torch.zeros(n, dtype=torch.float64, device="cuda"), torch.zeros(n, dtype=torch.float64, device="cuda")
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    ptrs = [s.cuda_stream for s in streams]
+    for rep in range(3):                                   # capture, replay, replay after a weight change
+        if rep == 2:
+            net.set_weights(scaled_weights(dims, 5))
+        net.eval_f16_dev_ptr(codes.data_ptr(), n, ref.data_ptr(), ptrs[0])
+        out.zero_()
+        net.eval_f16_dev_batches(codes.data_ptr(), n, 1024, out.data_ptr(), ptrs)     # 41 launches: the graph path
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref) and float(out.abs().max()) > 0
+    half = torch.zeros(n, dtype=torch.float64, device="cuda")
+    net.eval_f16_dev_batches(codes.data_ptr(), 20 * 1024, 1024, half.data_ptr(), ptrs)  # another size: another graph
+    torch.cuda.synchronize()
+    assert torch.equal(half[:20 * 1024], ref[:20 * 1024]) and float(half[20 * 1024:].abs().max()) == 0.0
