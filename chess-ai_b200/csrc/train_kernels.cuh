@@ -172,6 +172,41 @@ struct BackwardArgs {
   double *err_sum;           // += sum_b (T - y)^2 / 2
 };
 
+// psi = omega * f'(theta) on this warp's NBH tiles of a layer (network.cpp:252): omega sits in the pair buffer, the saved
+// activation a = f(theta) comes from global memory. ALL NBH activation loads are issued before the first one is used (the
+// accumulator registers are free at this point): one exposed L2 latency per layer boundary instead of one per tile
+// (ncu of the per-tile loop: long_scoreboard 5.2 warps per issue, DMMA pipe 52 % active).
+template <int NBH>
+__device__ __forceinline__ void psi_tiles(double2 *a_out, const double *__restrict__ acts, double *__restrict__ psis, size_t goff0, size_t stride,
+                                          int lane, bool valid) {
+  double2 av[NBH];
+#pragma unroll
+  for (int j = 0; j < NBH; ++j) {
+    av[j] = make_double2(0.0, 0.0);
+    if (valid) av[j] = __ldcg(reinterpret_cast<const double2 *>(acts + goff0 + (size_t) j * stride));
+  }
+#pragma unroll
+  for (int j = 0; j < NBH; ++j) {
+    double2 om = a_out[j * 32 + lane];
+    om.x = valid ? om.x * act_df_from_a(av[j].x) : 0.0;
+    om.y = valid ? om.y * act_df_from_a(av[j].y) : 0.0;
+    a_out[j * 32 + lane] = om;
+    *reinterpret_cast<double2 *>(psis + goff0 + (size_t) j * stride) = om;
+  }
+}
+#define CAB_NB_CASE(N) \
+  case N: psi_tiles<N>(a_out, acts, psis, goff0, stride, lane, valid); break;
+__device__ __forceinline__ void dispatch_psi(int nbh, double2 *a_out, const double *acts, double *psis, size_t goff0, size_t stride, int lane,
+                                             bool valid) {
+  switch (nbh) {
+    CAB_NB_CASE(1) CAB_NB_CASE(2) CAB_NB_CASE(3) CAB_NB_CASE(4) CAB_NB_CASE(5) CAB_NB_CASE(6) CAB_NB_CASE(7)
+    CAB_NB_CASE(8) CAB_NB_CASE(9) CAB_NB_CASE(10) CAB_NB_CASE(11) CAB_NB_CASE(12) CAB_NB_CASE(13) CAB_NB_CASE(14)
+    CAB_NB_CASE(15) CAB_NB_CASE(16)
+    default: break;
+  }
+}
+#undef CAB_NB_CASE
+
 __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const BackwardArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int n_stages = args.n_stages, stage_bytes = args.stage_bytes;
@@ -208,6 +243,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
   double2 *abuf = abuf_all + (size_t) pair * args.a_units * 32;
   const int m = lane >> 2, q = lane & 3;
   double acc[kMaxNBH][2];
+#pragma unroll
+  for (int j = 0; j < kMaxNBH; ++j) acc[j][0] = acc[j][1] = 0.0;
   uint32_t rs = 0, rk = 0;
   long n = 0;
   double err_local = 0.0;
@@ -237,13 +274,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
 
     for (int c = 0; c < args.n_chunks; ++c, ++n) {
       const ChunkDesc d = chunks[c];
-      const bool first = d.flags & kFirst, last = d.flags & kLast;
+      const bool last = d.flags & kLast;
       int j0, nbh;
       split_tiles(d.nb, d.layer, half, j0, nbh);
-      if (first) {
-#pragma unroll
-        for (int j = 0; j < kMaxNBH; ++j) acc[j][0] = acc[j][1] = 0.0;
-      }
       mbar_wait(&full[rs], rk & 1);
       dispatch_chunk(nbh, acc, abuf_addr + (uint32_t) (d.a_in + d.t0) * kUnitBytes,
                      ring_addr + rs * (uint32_t) stage_bytes + (uint32_t) j0 * kUnitBytes, (uint32_t) d.nb * kUnitBytes, d.tcount);
@@ -268,16 +301,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
         double2 *a_out = abuf + (size_t) (d.a_out + j0) * 32;
         pair_barrier(pair);
         dispatch_store(nbh, acc, a_out, lane);
-        for (int j = 0; j < nbh; ++j) {
-          const size_t goff = (size_t) (d.save_off + d.tile0 + j0 + j) * args.save_stride + lane_off;
-          double2 om = a_out[j * 32 + lane];
-          double2 av = make_double2(0.0, 0.0);
-          if (valid) av = *reinterpret_cast<const double2 *>(args.acts + goff);
-          om.x = valid ? om.x * act_df_from_a(av.x) : 0.0;
-          om.y = valid ? om.y * act_df_from_a(av.y) : 0.0;
-          a_out[j * 32 + lane] = om;
-          *reinterpret_cast<double2 *>(args.psis + goff) = om;
-        }
+#pragma unroll
+        for (int j = 0; j < kMaxNBH; ++j) acc[j][0] = acc[j][1] = 0.0;   // the next chunk starts a layer: zeroed HERE, so that the
+                                                                          // registers are visibly free for the loads below
+        dispatch_psi(nbh, a_out, args.acts, args.psis, (size_t) (d.save_off + d.tile0 + j0) * args.save_stride + lane_off, (size_t) args.save_stride,
+                     lane, valid);
         pair_barrier(pair);
       }
     }
