@@ -34,4 +34,14 @@ print("bf16 forward", wnet.predict_batch_bf16(codes[:130])[:2])
 print("bf16 train", cab.Optimizer.train_batch_bf16(wnet, codes[:200], t[:200], 2e-3))
 rec = synth.codes_to_records(codes[:7])
 print("encode", np.array_equal(cab.encode_records(rec), codes[:7]))
+print("fused f16", net.predict_batch_f16(codes[:300])[:2])   # 3 tiles on 3 CTAs; then one CTA walking several tiles is not reachable at this size
+import torch
+dc = torch.from_numpy(codes).cuda()
+dt = torch.from_numpy(t).cuda()
+st = torch.cuda.Stream()
+print("train_epoch_dev", cab.train_epoch_dev(student, dc.data_ptr(), dt.data_ptr(), 300, 128, 0.5, stream=st.cuda_stream))
+sp = cab.SelfPlay(net, games=4, playouts_per_move=16, roots=2, in_flight=4, max_moves=2, network_priors=1, noise=1, save_ratio=0.5, seed=3)
+print("selfplay", sp.run()["playouts"])
+sp.close()
+print("best_move", cab.best_move(net, np.array([4, 6, 7, 3, 1, 7, 6, 4] + [8] * 8 + [0] * 32 + [-8] * 8 + [-4, -6, -7, -3, -1, -7, -6, -4], dtype=np.int8), 1, "f16"))
 print("ok")
