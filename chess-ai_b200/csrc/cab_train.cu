@@ -224,6 +224,12 @@ static int launch_backward(cab_net *net, const double *d_targets, long b0, long 
   a.save_stride = net->train_cap * 8;
   a.out_unit = net->act_unit_off.back();
   a.err_sum = net->d_grad + net->n_weights;  // [sumE, sumE', count, spare]
+  a.blob = net->bwd.d_blob;
+  for (int st = 0; st < geo.n_stages && st < kMaxStages; ++st) {   // the ring's first fills, as kernel parameters
+    const ChunkDesc &cd = net->bwd.chunks[st % net->bwd.chunks.size()];
+    a.fill_off[st] = cd.src_off;
+    a.fill_bytes[st] = cd.bytes;
+  }
   const size_t smem = forward_smem_bytes(a.a_units, geo.n_cons, geo.n_stages, net->stage_bytes);
   const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * geo.ctas_per_sm);
   static std::atomic<uint64_t> attr_devices{0};   // the attribute is per device: one bit per device ordinal

@@ -170,6 +170,8 @@ struct BackwardArgs {
   uint32_t out_unit;         // unit offset of the output layer inside acts / psis
   int n_stages, stage_bytes;
   double *err_sum;           // += sum_b (T - y)^2 / 2
+  const uint8_t *blob;       // the plan's chunk table, fetched by one bulk copy
+  uint32_t fill_off[kMaxStages], fill_bytes[kMaxStages];   // the ring's first fills (no global read before the first fetch)
 };
 
 // psi = omega * f'(theta) on this warp's NBH tiles of a layer (network.cpp:252): omega sits in the pair buffer, the saved
@@ -214,34 +216,45 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
   uint8_t *ring = smem;
   double2 *abuf_all = reinterpret_cast<double2 *>(smem + fwd_smem_ring(n_stages, stage_bytes));
   ChunkDesc *s_chunks = reinterpret_cast<ChunkDesc *>(smem + fwd_smem_ring(n_stages, stage_bytes) + fwd_smem_abuf(n_pairs, args.a_units));
-  // same carve-up as the forward kernel (the 32 doubles after the chunk table are its exp table; unused here)
-  uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(s_chunks + kSmemChunks) + 32);
-  uint32_t *done = reinterpret_cast<uint32_t *>(full + n_stages);
+  // same carve-up as the forward kernel (its exp table and dot scratch lie between the chunk table and the barriers; unused here)
+  uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_chunks) + kBlobBytes + kDotScratchBytes);
+  uint64_t *tbl_bar = full + n_stages;
+  uint32_t *done = reinterpret_cast<uint32_t *>(tbl_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = warp >> 1, half = pair_half(warp);
+  const int m = lane >> 2, q = lane & 3;
   const long my_groups = args.n_groups > blockIdx.x ? (args.n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long total_chunks = my_groups * args.n_chunks;
   const bool table_in_smem = args.n_chunks <= kSmemChunks;
   const ChunkDesc *chunks = table_in_smem ? s_chunks : args.chunks;
-  if (table_in_smem) {
-    const int n16 = args.n_chunks * (int) (sizeof(ChunkDesc) / 16);
-    for (int i = threadIdx.x; i < n16; i += blockDim.x)
-      reinterpret_cast<int4 *>(s_chunks)[i] = reinterpret_cast<const int4 *>(args.chunks)[i];
+  // start-up trimmed like the forward kernel's (a CTA of an 8 192-board piece lives for one pass): the first group's
+  // output and target are requested before anything else, the chunk table arrives by one bulk copy, the first ring fills
+  // take their addresses from the kernel parameters
+  double y_first = 0.0, t_first = 0.0;
+  {
+    const long board0 = ((long) blockIdx.x * n_pairs + pair) * kBoardsPerWarp;
+    if (half == 0 && q == 0 && my_groups > 0 && board0 + m < args.n_boards) {
+      y_first = __ldcg(args.acts + (size_t) args.out_unit * args.save_stride + (size_t) board0 * 8 + lane * 2);
+      t_first = __ldg(args.targets + board0 + m);
+    }
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
+    mbar_init(tbl_bar, 1);
     mbar_fence_init();
     for (int s = 0; s < n_stages && s < total_chunks; ++s) {
-      const ChunkDesc *d = &args.chunks[s % args.n_chunks];
-      mbar_arrive_expect_tx(&full[s], d->bytes);
-      bulk_g2s(ring + (size_t) s * stage_bytes, args.pack + d->src_off, d->bytes, &full[s]);
+      mbar_arrive_expect_tx(&full[s], args.fill_bytes[s]);
+      bulk_g2s(ring + (size_t) s * stage_bytes, args.pack + args.fill_off[s], args.fill_bytes[s], &full[s]);
+    }
+    if (table_in_smem) {
+      mbar_arrive_expect_tx(tbl_bar, (uint32_t) kBlobChunkBytes);
+      bulk_g2s(s_chunks, args.blob, (uint32_t) kBlobChunkBytes, tbl_bar);
     }
   }
   __syncthreads();
 
   double2 *abuf = abuf_all + (size_t) pair * args.a_units * 32;
-  const int m = lane >> 2, q = lane & 3;
   double acc[kMaxNBH][2];
 #pragma unroll
   for (int j = 0; j < kMaxNBH; ++j) acc[j][0] = acc[j][1] = 0.0;
@@ -262,8 +275,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
     if (half == 0) {
       double2 psi = make_double2(0.0, 0.0);
       if (valid && q == 0) {
-        const double y = args.acts[(size_t) args.out_unit * args.save_stride + lane_off];
-        const double om = args.targets[board] - y;
+        const bool first_group = g == (long) blockIdx.x;
+        const double y = first_group ? y_first : args.acts[(size_t) args.out_unit * args.save_stride + lane_off];
+        const double om = (first_group ? t_first : args.targets[board]) - y;
         err_local += om * om / 2.0;
         psi.x = om * act_df_from_a(y);
       }
@@ -271,6 +285,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mlp_backward_kernel(const Back
       *reinterpret_cast<double2 *>(args.psis + (size_t) args.out_unit * args.save_stride + lane_off) = psi;
     }
     pair_barrier(pair);
+    if (table_in_smem && g == (long) blockIdx.x) mbar_wait(tbl_bar, 0);   // the chunk table has landed
 
     for (int c = 0; c < args.n_chunks; ++c, ++n) {
       const ChunkDesc d = chunks[c];
