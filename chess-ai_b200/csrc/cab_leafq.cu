@@ -204,26 +204,36 @@ int cab_leafq_stats(cab_leafq *q, long *launches, long *flushes, long *evaluated
 }
 
 // K7 on host arrays: n_seg nodes, node s owns logits[seg_off[s] .. seg_off[s+1]) and colour multiplier color_mult[s]
+// Stand-alone K7 for callers that keep their search on the host (inside cab_mcts_* it is fused into the walk kernel). The
+// device scratch is one grow-only block per calling thread and device: no allocation in the steady state.
 int cab_prior_softmax_host(int device, const double *logits, const int *seg_off, int n_seg, const double *color_mult,
                            double *priors_out) {
   if (n_seg < 0 || (n_seg > 0 && (!logits || !seg_off || !color_mult || !priors_out))) { set_error("bad argument"); return CAB_EINVAL; }
   if (n_seg == 0) return CAB_OK;
   CAB_CUDA(cudaSetDevice(device));
   const int total = seg_off[n_seg];
-  double *d_l = nullptr, *d_p = nullptr, *d_c = nullptr;
-  int *d_o = nullptr;
-  CAB_CUDA(cudaMalloc(&d_l, (size_t) std::max(total, 1) * sizeof(double)));
-  CAB_CUDA(cudaMalloc(&d_p, (size_t) std::max(total, 1) * sizeof(double)));
-  CAB_CUDA(cudaMalloc(&d_c, (size_t) n_seg * sizeof(double)));
-  CAB_CUDA(cudaMalloc(&d_o, (size_t) (n_seg + 1) * sizeof(int)));
-  CAB_CUDA(cudaMemcpy(d_l, logits, (size_t) total * sizeof(double), cudaMemcpyHostToDevice));
-  CAB_CUDA(cudaMemcpy(d_c, color_mult, (size_t) n_seg * sizeof(double), cudaMemcpyHostToDevice));
-  CAB_CUDA(cudaMemcpy(d_o, seg_off, (size_t) (n_seg + 1) * sizeof(int), cudaMemcpyHostToDevice));
-  prior_softmax_kernel<<<(n_seg * 32 + 255) / 256, 256>>>(d_l, d_o, n_seg, d_c, d_p);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpy(priors_out, d_p, (size_t) total * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(d_l); cudaFree(d_p); cudaFree(d_c); cudaFree(d_o);
-  if (e != cudaSuccess) return cuda_fail(e, "prior_softmax", __FILE__, __LINE__);
+  if (total < 0) { set_error("seg_off must be non-decreasing"); return CAB_EINVAL; }
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t b_l = up((size_t) std::max(total, 1) * sizeof(double)), b_c = up((size_t) n_seg * sizeof(double)),
+               b_o = up((size_t) (n_seg + 1) * sizeof(int));
+  const size_t need = 2 * b_l + b_c + b_o;
+  thread_local struct { int device = -1; size_t cap = 0; uint8_t *p = nullptr; } scratch;
+  if (scratch.device != device || scratch.cap < need) {
+    if (scratch.p != nullptr) { cudaSetDevice(scratch.device); cudaFree(scratch.p); cudaSetDevice(device); }
+    scratch.p = nullptr; scratch.cap = 0; scratch.device = device;
+    CAB_CUDA(cudaMalloc(&scratch.p, need + need / 2));
+    scratch.cap = need + need / 2;
+  }
+  double *d_l = reinterpret_cast<double *>(scratch.p), *d_p = reinterpret_cast<double *>(scratch.p + b_l),
+         *d_c = reinterpret_cast<double *>(scratch.p + 2 * b_l);
+  int *d_o = reinterpret_cast<int *>(scratch.p + 2 * b_l + b_c);
+  CAB_CUDA(cudaMemcpyAsync(d_l, logits, (size_t) total * sizeof(double), cudaMemcpyHostToDevice, cudaStreamPerThread));
+  CAB_CUDA(cudaMemcpyAsync(d_c, color_mult, (size_t) n_seg * sizeof(double), cudaMemcpyHostToDevice, cudaStreamPerThread));
+  CAB_CUDA(cudaMemcpyAsync(d_o, seg_off, (size_t) (n_seg + 1) * sizeof(int), cudaMemcpyHostToDevice, cudaStreamPerThread));
+  prior_softmax_kernel<<<(n_seg * 32 + 255) / 256, 256, 0, cudaStreamPerThread>>>(d_l, d_o, n_seg, d_c, d_p);
+  CAB_CUDA(cudaGetLastError());
+  CAB_CUDA(cudaMemcpyAsync(priors_out, d_p, (size_t) total * sizeof(double), cudaMemcpyDeviceToHost, cudaStreamPerThread));
+  CAB_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
   return CAB_OK;
 }
 
