@@ -84,6 +84,7 @@ _SIGS = {
     "cab_train_batch_host": [_vp, _i8p, _f64p, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp],
     "cab_train_batch_dev": [_vp, _vp, _vp, C.c_long, _dp, C.c_double, C.c_double, _ip, _dp, _dp, _vp],
     "cab_train_epoch_dev": [_vp, _vp, _vp, C.c_long, C.c_long, _dp, C.c_double, C.c_double, C.c_int, C.c_uint64, _vp, _vp, _vp],
+    "cab_train_epoch_host": [_vp, _i8p, _f64p, C.c_long, C.c_long, _dp, C.c_double, C.c_double, C.c_int, C.c_uint64, _vp, _vp],
     "cab_train_epoch_bf16_dev": [_vp, _vp, _vp, C.c_long, C.c_long, _dp, C.c_double, C.c_double, C.c_int, C.c_uint64, _vp, _vp, _vp],
     "cab_dropout": [_vp, C.c_double, C.c_uint64, C.c_uint64, _lp],
     "cab_dp_unique_id": [_vp],

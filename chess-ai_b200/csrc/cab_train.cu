@@ -687,6 +687,20 @@ int cab_train_epoch_dev(cab_net *net, const int8_t *codes_dev, const double *tar
                           stream ? (cudaStream_t) stream : net->train_stream, false);
 }
 
+int cab_train_epoch_host(cab_net *net, const int8_t *codes_host, const double *targets_host, long n_cases, long batch, double *lambda,
+                         double max_const, double rate, int reset_rule, uint64_t dropout_seed, cab_train_stats *stats, double *e_trace_host) {
+  if (!net || !lambda || n_cases <= 0 || batch <= 0 || !codes_host || !targets_host) { set_error("bad argument"); return CAB_EINVAL; }
+  CAB_CUDA(cudaSetDevice(net->device));
+  int rc = ensure_train_state(net);
+  if (rc != CAB_OK) return rc;
+  if ((rc = ensure_host_staging(net, n_cases)) != CAB_OK) return rc;
+  cudaStream_t s = net->train_stream;
+  CAB_CUDA(cudaMemcpyAsync(net->d_tcodes, codes_host, (size_t) n_cases * 64, cudaMemcpyHostToDevice, s));
+  CAB_CUDA(cudaMemcpyAsync(net->d_ttargets, targets_host, (size_t) n_cases * sizeof(double), cudaMemcpyHostToDevice, s));
+  return train_epoch_impl(net, net->d_tcodes, net->d_ttargets, n_cases, batch, lambda, max_const, rate, reset_rule, dropout_seed, stats, e_trace_host,
+                          s, false);
+}
+
 int cab_train_epoch_bf16_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases, long batch, double *lambda,
                              double max_const, double rate, int reset_rule, uint64_t dropout_seed, cab_train_stats *stats, double *e_trace_host,
                              void *stream) {

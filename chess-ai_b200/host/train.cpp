@@ -5,7 +5,7 @@
 // GAMES_PER_NETWORK_SAVE cases NetworkStorage::saveNetwork (network.cpp:345-364): rename latest.txt -> gen-<N>.txt,
 // write the new latest.txt.
 //   mode "exact": that loop verbatim, one case per step, executed on the device by cab_train_sequence
-//   mode "batch": the minibatch extension (cab_train_batch_host), same lambda / dropout rule applied per step
+//   mode "batch": the minibatch extension as resident epochs (cab_train_epoch_host), same lambda / dropout rule per step, on the device
 // Beyond the reference: lambda, the step count and the generation number persist in <out_dir>/trainer_state.txt, so a
 // restarted trainer continues instead of starting again at lambda0 and overwriting gen-0 (the reference loses both).
 //
@@ -144,19 +144,20 @@ int main(int argc, char **argv) {
       if (writer && n == save_every) CK(rotate(net, out_dir, st));
     }
   } else {
-    for (long s = 0; s < steps; ++s) {
-      draw(batch);
-      int acc = 0;
-      double e0 = 0.0, e1 = 0.0;
-      CK(cab_train_batch_host(net, codes.data(), targets.data(), batch, &st.lambda, 15.0, 1.1, &acc, &e0, &e1));
-      if (first_err < 0.0) first_err = e0;
-      last_err = acc ? e1 : e0;
-      accepted += acc; ++decisions; samples += batch; ++st.steps;
-      if (st.lambda < 1e-4 || st.lambda > 10.0) {          // train.cpp:54-57
-        st.lambda = 2.0;
-        CK(cab_dropout(net, 0.01, seed, (uint64_t) st.resets, nullptr));
-        ++st.resets;
-      }
+    // one save interval at a time: its minibatches are drawn on the host, uploaded once and trained as a RESIDENT epoch
+    // (cab_train_epoch_host: lambda, accept / reject, rollback and the reset + dropout rule of train.cpp:54-57 on the device)
+    codes.resize((size_t) save_every * batch * 64);
+    targets.resize((size_t) save_every * batch);
+    for (long done = 0; done < steps;) {
+      const long n_steps = std::min(save_every - st.steps % save_every, steps - done);
+      draw(n_steps * batch);
+      cab_train_stats ts;
+      CK(cab_train_epoch_host(net, codes.data(), targets.data(), n_steps * batch, batch, &st.lambda, 15.0, 1.1, 1,
+                              seed + (unsigned long long) st.resets, &ts, nullptr));
+      if (first_err < 0.0) first_err = ts.first_err;
+      last_err = ts.last_accepted ? ts.last_new_err : ts.last_err;
+      accepted += ts.accepted; decisions += ts.steps; samples += n_steps * batch; done += n_steps;
+      st.steps += n_steps; st.resets += ts.resets;
       if (writer && st.steps % save_every == 0) CK(rotate(net, out_dir, st));
     }
   }

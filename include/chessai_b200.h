@@ -240,6 +240,11 @@ typedef struct cab_train_stats {
 CAB_API int cab_train_epoch_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases, long batch,
                                 double *lambda, double max_const, double rate, int reset_rule, uint64_t dropout_seed,
                                 cab_train_stats *stats, double *e_trace_host, void *stream);
+/* the same with the cases in HOST memory: one upload, then the resident epoch (what the trainer command line calls per
+ * save interval) */
+CAB_API int cab_train_epoch_host(cab_net *net, const int8_t *codes_host, const double *targets_host, long n_cases, long batch,
+                                 double *lambda, double max_const, double rate, int reset_rule, uint64_t dropout_seed,
+                                 cab_train_stats *stats, double *e_trace_host);
 CAB_API int cab_train_epoch_bf16_dev(cab_net *net, const int8_t *codes_dev, const double *targets_dev, long n_cases, long batch,
                                      double *lambda, double max_const, double rate, int reset_rule, uint64_t dropout_seed,
                                      cab_train_stats *stats, double *e_trace_host, void *stream);
