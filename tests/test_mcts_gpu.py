@@ -146,3 +146,22 @@ def test_self_play_with_the_fp16_evaluator_keeps_the_search_invariants(cab, net)
     sp.close()
     with pytest.raises(cab.CabError):
         cab.SelfPlay(net, games=1, playouts_per_move=8, precision=7)
+
+
+def test_self_play_is_deterministic_for_a_seed(cab, net):
+    """Trees are walked one warp per tree with the playouts of a tree in order, requests are served in whatever order the
+    hardware schedules them: the GAMES must not depend on that order. Same seed -> the same positions, results and cases."""
+    def play(seed):
+        sp = cab.SelfPlay(net, games=24, playouts_per_move=64, roots=2, in_flight=8, max_moves=6, network_priors=1, noise=1, save_ratio=0.5, seed=seed)
+        st = sp.run()
+        states = [sp.game_state(i) for i in range(24)]
+        codes, targets = sp.cases()
+        order = np.lexsort(np.concatenate([codes.astype(np.int16), (targets[:, None] * 1e6).astype(np.int64)], axis=1).T[::-1])
+        sp.close()
+        return st, states, codes[order], targets[order]
+    a, b, c = play(11), play(11), play(12)
+    assert a[0]["playouts"] == b[0]["playouts"] and a[0]["boards_evaluated"] == b[0]["boards_evaluated"]
+    for x, y in zip(a[1], b[1]):
+        assert np.array_equal(x["codes"], y["codes"]) and (x["side"], x["over"], x["result"], x["moves_played"]) == (y["side"], y["over"], y["result"], y["moves_played"])
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert any(not np.array_equal(x["codes"], y["codes"]) for x, y in zip(a[1], c[1]))     # another seed: other games
