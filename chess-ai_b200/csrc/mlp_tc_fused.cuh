@@ -7,7 +7,8 @@
 //   * ALL weights live in shared memory for the whole kernel (fp16, zero-padded, pre-swizzled by f16_pack_kernel into
 //     the K-major SWIZZLE_128B image tcgen05 reads through shared-memory descriptors): 167 KB for the default net,
 //     fetched once per CTA with TMA bulk copies
-//   * activations never touch shared or global memory: the A operand of layers 1 and 2 is read FROM TENSOR MEMORY
+//   * activations never touch shared or global memory (the board itself is staged in shared memory as layer 0's A operand):
+//     the A operand of layers 1 and 2 is read FROM TENSOR MEMORY
 //     (tcgen05.mma ... [d], [a], b_desc: SASS UTCHMMA with a TMEM A operand). A layer's accumulator row is loaded by its
 //     thread (tcgen05.ld), put through the activation (carried as tanh(x/4), see act_pack_f32), packed to fp16 and
 //     stored back IN PLACE (tcgen05.st) as the next layer's A row — lane t only ever touches lane t: no shuffle, no layout change
@@ -37,7 +38,8 @@ struct FusedArgs {
   const int8_t *codes;        // [n_boards][64]
   long n_boards;
   double *out;                // [n_boards]
-  long long *prof;            // optional [grid][2][16] clock stamps of the CTA's second tile (CAB_F16_PROFILE debug launches)
+  long long *prof;            // optional [grid][64] clock stamps of the CTA's second tile: epilogue warp 0 [0, 16), MMA thread [16, 32),
+                              // epilogue 1 end / start per warp [32, 48) / [48, 64) (CAB_F16_PROFILE debug launches)
 };
 
 // kind::f16 instruction descriptor: D fp32 (bit 4), A and B fp16 (formats 0), K-major both, N >> 3 at bit 17, M = 128
