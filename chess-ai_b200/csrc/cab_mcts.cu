@@ -38,6 +38,7 @@ namespace mcts {
 constexpr int kDepth = 8;             // tree.cpp:145 SIMULATION_SEARCH_DEPTH
 constexpr int kMaxChildren = 256;     // fastchess kMaxMoves
 constexpr int kWarpsPerCta = 4;
+constexpr long kEvalPiece = 8192;     // boards per evaluator launch when a round's boards are spread over several streams
 constexpr int kBoardStride = 68;      // lane-private child boards: 17 words apart, so one square of all lanes hits 32 banks
 
 enum NodeFlags : uint8_t { kExpanded = 1, kPending = 2, kEval = 4 };
@@ -710,6 +711,8 @@ struct cab_mcts {
   Dev d{};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t eval_stream[4] = {};      // a round's boards are evaluated in pieces over these (fork / join on `stream`)
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
   double *d_pf = nullptr, *d_sig = nullptr;
   int *h_count = nullptr;         // pinned: boards queued by the last round
   long rounds = 0;
@@ -726,6 +729,9 @@ static void mcts_free(cab_mcts *q) {
   cudaFree(q->d_pf); cudaFree(q->d_sig);
   if (q->h_count) cudaFreeHost(q->h_count);
   if (q->stream) cudaStreamDestroy(q->stream);
+  for (auto st : q->eval_stream) if (st) cudaStreamDestroy(st);
+  for (auto e : q->ev_join) if (e) cudaEventDestroy(e);
+  if (q->ev_fork) cudaEventDestroy(q->ev_fork);
   if (q->ev0) cudaEventDestroy(q->ev0);
   if (q->ev1) cudaEventDestroy(q->ev1);
   delete q;
@@ -775,6 +781,11 @@ static int mcts_build(cab_mcts *q) {
   CAB_CUDA(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
   CAB_CUDA(cudaEventCreate(&q->ev0));
   CAB_CUDA(cudaEventCreate(&q->ev1));
+  CAB_CUDA(cudaEventCreateWithFlags(&q->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 4; ++i) {
+    CAB_CUDA(cudaStreamCreateWithFlags(&q->eval_stream[i], cudaStreamNonBlocking));
+    CAB_CUDA(cudaEventCreateWithFlags(&q->ev_join[i], cudaEventDisableTiming));
+  }
   // default: every game from the start position
   std::vector<GameState> gs(p.games);
   static const int8_t back[8] = {4, 6, 7, 3, 1, 7, 6, 4};
@@ -877,8 +888,22 @@ int cab_mcts_run(cab_mcts *q, int search_only, long max_rounds, cab_mcts_stats *
     if (n_boards > 0) {
       CAB_CUDA(cudaEventRecord(q->ev0, q->stream));
       // precision 1: the fused fp16 tcgen05 evaluator (reduced precision: the search is then NOT the reference's, see the header)
-      const int rc = q->prm.precision == 1 ? cab_eval_f16_dev(net, d.eval_codes[buf], n_boards, d.eval_out[buf], q->stream)
-                                           : launch_forward(net, d.eval_codes[buf], n_boards, d.eval_out[buf], nullptr, 0, q->stream, nullptr, /*alone=*/true);
+      int rc;
+      if (q->prm.precision == 1) {
+        rc = cab_eval_f16_dev(net, d.eval_codes[buf], n_boards, d.eval_out[buf], q->stream);
+      } else if (n_boards <= 2 * kEvalPiece) {
+        rc = launch_forward(net, d.eval_codes[buf], n_boards, d.eval_out[buf], nullptr, 0, q->stream, nullptr, /*alone=*/true);
+      } else {
+        // a big round as pieces over four streams: one persistent launch has every CTA ask for the same weight chunk at the
+        // same moment (1.62e8 boards/s), desynchronised pieces do not (1.95e8)
+        CAB_CUDA(cudaEventRecord(q->ev_fork, q->stream));
+        for (auto st : q->eval_stream) CAB_CUDA(cudaStreamWaitEvent(st, q->ev_fork, 0));
+        rc = cab_eval_dev_batches(net, d.eval_codes[buf], n_boards, kEvalPiece, d.eval_out[buf], reinterpret_cast<void *const *>(q->eval_stream), 4);
+        for (int i = 0; i < 4 && rc == CAB_OK; ++i) {
+          CAB_CUDA(cudaEventRecord(q->ev_join[i], q->eval_stream[i]));
+          CAB_CUDA(cudaStreamWaitEvent(q->stream, q->ev_join[i], 0));
+        }
+      }
       if (rc != CAB_OK) return rc;
       CAB_CUDA(cudaEventRecord(q->ev1, q->stream));
       CAB_CUDA(cudaEventSynchronize(q->ev1));

@@ -220,3 +220,21 @@ def test_epoch_on_the_device_equals_step_by_step(cab, golden):
     assert np.abs(trace - hist).max() <= 1e-9 * np.abs(hist).max()          # fp64 sums in atomic order: rounding only
     assert st["first_err"] == trace[0, 0] and st["last_err"] == trace[-1, 0]
     assert np.abs(a.get_weights() - b.get_weights()).max() <= 1e-9
+
+
+def test_epoch_from_host_memory_equals_the_resident_epoch(cab, golden):
+    """cab_train_epoch_host (what the trainer command line calls per save interval) = one upload + cab_train_epoch_dev."""
+    import ctypes as C
+    import torch
+    synth = importlib.import_module("chess-ai_b200.synth")
+    n, batch = 3 * 2048 + 300, 2048
+    codes = synth.synthetic_boards(n, seed=6)
+    targets = cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"]).predict_batch(codes)
+    w0 = cab.Network.randomNetwork(DEFAULT_DIMS, seed=78).get_weights() * 0.05
+    a, b = cab.Network.from_weights(DEFAULT_DIMS, w0), cab.Network.from_weights(DEFAULT_DIMS, w0)
+    d_codes, d_targets = torch.from_numpy(codes).cuda(), torch.from_numpy(targets).cuda()
+    lam_a, st_a = cab.train_epoch_dev(a, d_codes.data_ptr(), d_targets.data_ptr(), n, batch, 1.0, dropout_seed=5)
+    st_b, lam_b = cab.TrainStats(), C.c_double(1.0)
+    cab._ck(cab.lib().cab_train_epoch_host(b._h, codes.reshape(-1), targets, n, batch, C.byref(lam_b), 15.0, 1.1, 1, 5, C.byref(st_b), None))
+    assert lam_b.value == lam_a and st_b.as_dict()["steps"] == st_a["steps"] == 4 and st_b.as_dict()["accepted"] == st_a["accepted"]
+    assert np.abs(a.get_weights() - b.get_weights()).max() <= 1e-9
