@@ -30,30 +30,50 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 
 // K0 board encoder: piece records -> int8 codes. Integer-only, bit-exact with Piece::code()/0.4
 // (/root/reference/src/chess/piece.cpp:103-105,145-147,179-181,260-262; type/colour tables piece.fwd.h:122-133,287-308).
-// HBM-bound byte kernel: 192 B in, 64 B out per board; each thread encodes 4 squares (12 B in as 3 words, 4 B out).
-__global__ void __launch_bounds__(256) encode_kernel(const uint32_t *__restrict__ rec_words, long n_quads,
-                                                      uint32_t *__restrict__ codes_words) {
+// HBM-bound byte kernel: 192 B in, 64 B out per board. A CTA takes 64 boards (12 KB of records): the records arrive
+// by three fully coalesced 16-byte loads per thread into shared memory, a thread then encodes 16 consecutive squares
+// (48 B from shared memory at a 12-word stride: conflict-free for 128-bit accesses) and stores one 16-byte word.
+constexpr int kEncThreads = 256;  // 16 squares per thread = 64 boards per CTA
+__device__ __forceinline__ int encode_square(uint32_t type, uint32_t color, uint32_t flag) {
   // base code by type: none 0, king 1, queen 3, rook 4, knight 6, bishop 7, pawn 8; flag adds 1 for king/rook/pawn
-  for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n_quads; i += (long) gridDim.x * blockDim.x) {
-    const uint32_t w0 = rec_words[3 * i], w1 = rec_words[3 * i + 1], w2 = rec_words[3 * i + 2];
-    const uint64_t lo = ((uint64_t) w1 << 32) | w0;
-    uint32_t outw = 0;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      // bytes 3s, 3s+1, 3s+2 of the 12-byte group
-      const int b0 = 3 * s;
-      auto byte_at = [&](int b) -> uint32_t { return b < 8 ? (uint32_t) (lo >> (8 * b)) & 0xffu : (w2 >> (8 * (b - 8))) & 0xffu; };
-      const uint32_t type = byte_at(b0), color = byte_at(b0 + 1), flag = byte_at(b0 + 2);
-      int k = 0;
-      if (type >= 1 && type <= 6 && (color == 1 || color == 2)) {
-        k = (int) ((0x876431u >> (4 * (type - 1))) & 0xfu);  // nibbles: king 1, queen 3, rook 4, knight 6, bishop 7, pawn 8
-        if (flag != 0 && (type == 1 || type == 3 || type == 6)) k += 1;
-        if (color == 2) k = -k;
-      }
-      outw |= ((uint32_t) (uint8_t) (int8_t) k) << (8 * s);
-    }
-    codes_words[i] = outw;
+  int k = 0;
+  if (type >= 1 && type <= 6 && (color == 1 || color == 2)) {
+    k = (int) ((0x876431u >> (4 * (type - 1))) & 0xfu);  // nibbles: king 1, queen 3, rook 4, knight 6, bishop 7, pawn 8
+    if (flag != 0 && (type == 1 || type == 3 || type == 6)) k += 1;
+    if (color == 2) k = -k;
   }
+  return k;
+}
+__global__ void __launch_bounds__(kEncThreads) encode_kernel(const uint4 *__restrict__ rec, long n_hex,
+                                                              uint4 *__restrict__ codes) {
+  __shared__ uint4 sh[3 * kEncThreads];
+  const long hex0 = (long) blockIdx.x * kEncThreads;            // first 16-square group of this CTA
+  const long n_in = min((long) kEncThreads, n_hex - hex0) * 3;  // 16-byte words of records this CTA owns
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int idx = threadIdx.x + j * kEncThreads;
+    if (idx < n_in) sh[idx] = __ldcs(rec + 3 * hex0 + idx);     // read once: streaming load
+  }
+  __syncthreads();
+  if (hex0 + threadIdx.x >= n_hex) return;
+  uint32_t w[12];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const uint4 v = sh[3 * threadIdx.x + j];
+    w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {  // four squares = 12 bytes = words 3q .. 3q+2
+    const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+    const int k0 = encode_square(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
+    const int k1 = encode_square(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
+    const int k2 = encode_square((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
+    const int k3 = encode_square((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
+    o[q] = (uint32_t) (uint8_t) k0 | ((uint32_t) (uint8_t) k1 << 8) | ((uint32_t) (uint8_t) k2 << 16) |
+           ((uint32_t) (uint8_t) k3 << 24);
+  }
+  __stcs(codes + hex0 + threadIdx.x, make_uint4(o[0], o[1], o[2], o[3]));
 }
 
 // weights -> DMMA B-fragment stream (see cab_internal.cuh). One thread per packed double.
@@ -697,10 +717,15 @@ int cab_net_dump_text(const cab_net *net, const char *path) {
 int cab_encode_dev(const uint8_t *records_dev, long n_boards, int8_t *codes_dev, void *stream) {
   if (n_boards < 0 || (n_boards > 0 && (!records_dev || !codes_dev))) { set_error("bad argument"); return CAB_EINVAL; }
   if (n_boards == 0) return CAB_OK;
-  const long quads = n_boards * 16;
-  const int grid = (int) std::min<long>((quads + 255) / 256, 148L * 16);
-  encode_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(reinterpret_cast<const uint32_t *>(records_dev), quads,
-                                                         reinterpret_cast<uint32_t *>(codes_dev));
+  const long n_hex = n_boards * 4;  // groups of 16 squares
+  if ((reinterpret_cast<uintptr_t>(records_dev) | reinterpret_cast<uintptr_t>(codes_dev)) & 15) {
+    set_error("encoder buffers must be 16-byte aligned");
+    return CAB_EINVAL;
+  }
+  const long grid = (n_hex + kEncThreads - 1) / kEncThreads;
+  if (grid > 0x7fffffffL) { set_error("too many boards for one encoder launch"); return CAB_EINVAL; }
+  encode_kernel<<<(unsigned) grid, kEncThreads, 0, (cudaStream_t) stream>>>(
+      reinterpret_cast<const uint4 *>(records_dev), n_hex, reinterpret_cast<uint4 *>(codes_dev));
   CAB_CUDA(cudaGetLastError());
   return CAB_OK;
 }

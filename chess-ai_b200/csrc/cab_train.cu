@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 
@@ -128,23 +129,34 @@ struct GradPlan {
 static std::mutex g_plan_mu;
 static std::vector<std::pair<cab_net *, GradPlan>> g_grad_plans;
 
-// Splits n boards (rounded up to 4) of every task into warp-sized items of about equal DMMA work: a task's number of
-// slices is proportional to its tile count. Board ranges start on stage boundaries (multiples of kGradStageBoards).
+// Splits the n boards (rounded up to 4) into slices and every slice into one item per task (a warp's unit of work).
+// Items are ordered SLICE-MAJOR: the persistent warps draw them in order, so the ~1 200 items in flight at any moment
+// cover the same few dozen board slices and every saved-activation / psi unit a slice needs is read from DRAM once and
+// from L2 by the other tile blocks that contract over it (task-major order, round 2's first form, re-read the units
+// once per tile block that needs them: 1.1 GB per 65 536 boards against 0.53 GB of operands, L2 hit 50 %). Inside a
+// slice the expensive blocks come first, so the last items drawn are the thin ones. Slices start on stage boundaries
+// (multiples of kGradStageBoards) and shrink with the batch so that a small batch still yields ~4 items per warp.
 static int build_grad_items(cab_net *net, GradPlan &gp, long n) {
   if (gp.items_n == n) return CAB_OK;
   const long n4 = (n + 3) / 4 * 4;
-  double wsum = 0.0;
-  // cost model of a block per board: its DMMAs, but never less than the copy-latency floor of a thin block
-  auto cost = [](const GradTask &t) { return std::max(t.nkt * t.nnt + 2.0, 10.0); };
-  for (auto &t : gp.tasks) wsum += cost(t);
+  static const long env_slice = getenv("CAB_GRAD_SLICE") ? atol(getenv("CAB_GRAD_SLICE")) : 256;
+  static const bool task_major = getenv("CAB_GRAD_TASK_MAJOR") != nullptr;   // the old order, kept for A/B timing
   const double target_items = (double) net->sm_count * kGradWarps * 4;
+  const long slices_wanted = std::max<long>(1, std::lround(target_items / std::max(1, gp.n_tasks)));
+  long per = std::min<long>(std::max<long>(64, env_slice), std::max<long>(64, (n4 + slices_wanted - 1) / slices_wanted));
+  per = (per + kGradStageBoards - 1) / kGradStageBoards * kGradStageBoards;
+  std::vector<int> order(gp.n_tasks);
+  for (int i = 0; i < gp.n_tasks; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    return gp.tasks[x].nkt * gp.tasks[x].nnt > gp.tasks[y].nkt * gp.tasks[y].nnt;
+  });
   std::vector<GradItem> items;
-  for (int ti = 0; ti < gp.n_tasks; ++ti) {
-    const GradTask &t = gp.tasks[ti];
-    long slices = std::max<long>(1, std::lround(target_items * cost(t) / wsum));
-    long per = std::max<long>(64, (n4 + slices - 1) / slices);
-    per = (per + kGradStageBoards - 1) / kGradStageBoards * kGradStageBoards;
-    for (long b = 0; b < n4; b += per) items.push_back(GradItem{ti, (int) b, (int) std::min(b + per, n4), 0});
+  if (!task_major) {
+    for (long b = 0; b < n4; b += per)
+      for (int ti : order) items.push_back(GradItem{ti, (int) b, (int) std::min(b + per, n4), 0});
+  } else {
+    for (int ti = 0; ti < gp.n_tasks; ++ti)
+      for (long b = 0; b < n4; b += per) items.push_back(GradItem{ti, (int) b, (int) std::min(b + per, n4), 0});
   }
   cudaFree(gp.d_items);
   gp.d_items = nullptr;

@@ -85,6 +85,7 @@ CAB_API int cab_net_dump_text(const cab_net *net, const char *path);
 
 /* ---- encoder (Network::loadBoard + Piece::code  network.cpp:119-123) ------------------------------------------ */
 CAB_API int cab_encode_host(int device, const uint8_t *records_host, long n_boards, int8_t *codes_host);
+/* Device buffers must be 16-byte aligned (any cudaMalloc pointer, any whole-board offset into one). */
 CAB_API int cab_encode_dev(const uint8_t *records_dev, long n_boards, int8_t *codes_dev, void *stream);
 
 /* ---- forward (Network::predictPosition  network.cpp:92-117), fp64 reference-precision path --------------------- */

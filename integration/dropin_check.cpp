@@ -4,7 +4,10 @@
 // network::load_training_case + Optimizer::optimize, operator<<, tree::MCTS::run_mcts_multithreaded.
 // Prints one JSON object; tests/test_dropin_gpu.py compares it with the golden values of the reference's CPU network.
 //
-//   dropin_check <latest.txt> <start_position.txt> <case.txt> <dump_out.txt> [mcts_sims]
+//   dropin_check <latest.txt> <start_position.txt> <case.txt> <dump_out.txt> [mcts_sims] [rotate]
+// With "rotate" NetworkStorage::SAVE_NETWORKS is on from the start (initialization.cpp:192): initialize() writes
+// network_dump/latest.txt, saveNetwork() / flushStorage() rotate it to gen-0.txt, gen-1.txt (network.cpp:345-364); the
+// directory network_dump/ must exist under the working directory.
 #include <cstdio>
 #include <fstream>
 #include <string>
@@ -17,6 +20,8 @@
 
 int main(int argc, char **argv) {
   if (argc < 5) { std::fprintf(stderr, "usage: %s latest.txt start.txt case.txt dump_out.txt [mcts_sims]\n", argv[0]); return 2; }
+  const bool rotate = argc > 6 && std::string(argv[6]) == "rotate";
+  network::NetworkStorage::SAVE_NETWORKS = rotate;
   network::Network *net = network::NetworkStorage::initialize(std::string(argv[1]));
 
   // Decider::prediction on the start position (decider.cpp:31-61) — reference code calling our predictPosition
@@ -36,6 +41,8 @@ int main(int argc, char **argv) {
 
   // byte-exact dump through operator<<
   { std::ofstream out(argv[4]); out << copy; }
+
+  if (rotate) network::NetworkStorage::saveNetwork();   // latest.txt -> gen-0.txt, the optimised network -> latest.txt
 
   // the reference's root-parallel MCTS (tree.cpp:149-196) searching with our evaluator from 2 threads
   int sims = argc > 5 ? std::atoi(argv[5]) : 0;

@@ -34,3 +34,22 @@ def test_reference_engine_runs_on_the_b200_network(cab, golden, tmp_path):
     assert os.path.getsize(dump) == g["latest_txt"]["bytes"]
     again = cab.Network.loadFromFile(dump)
     assert np.abs(again.get_weights() - golden["latest_weights"]).max() < 1e-12
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="integration/_build/dropin_check not built (needs /root/reference)")
+def test_checkpoint_rotation_through_the_shim(cab, golden, tmp_path):
+    """NetworkStorage with SAVE_NETWORKS = true, driven through the reference's own header (network.cpp:345-364):
+    initialize(path) writes network_dump/latest.txt, saveNetwork() renames it to gen-0.txt and writes the current network,
+    flushStorage() rotates once more. Every file is the reference's text format, byte for byte."""
+    latest = str(tmp_path / "in.txt")
+    cab.Network.from_weights(DEFAULT_DIMS, golden["latest_weights"]).dump(latest)
+    os.mkdir(str(tmp_path / "network_dump"))
+    subprocess.check_output([BIN, latest, os.path.join(GOLDEN, "start_position.txt"), os.path.join(GOLDEN, "board_20.txt"),
+                             str(tmp_path / "after.txt"), "0", "rotate"], cwd=str(tmp_path), timeout=300)
+    d = tmp_path / "network_dump"
+    assert sorted(os.listdir(str(d))) == ["gen-0.txt", "gen-1.txt", "latest.txt"]
+    assert (d / "gen-0.txt").read_bytes() == open(latest, "rb").read()          # what initialize(path) saved: the loaded network
+    assert (d / "gen-1.txt").read_bytes() == (d / "latest.txt").read_bytes()    # saveNetwork(), then flushStorage(): same network
+    assert (d / "latest.txt").read_bytes() == (tmp_path / "after.txt").read_bytes()   # operator<< of the clone
+    w = cab.Network.loadFromFile(str(d / "latest.txt")).get_weights()
+    assert np.abs(w - golden["latest_weights"]).max() < 1e-12                   # the rejected step's W += d; W -= d rounding only

@@ -48,6 +48,20 @@ def test_encoder_random_boards_bit_exact(cab, port, golden):
     assert np.array_equal(port.encode_records(recs), golden["syn_codes"])
 
 
+@pytest.mark.parametrize("n", [1, 3, 63, 64, 65, 127, 1000, 4097])
+def test_encoder_ragged_sizes_bit_exact(cab, port, n):
+    # the kernel takes 64 boards per CTA and 16 squares per thread: sizes around those edges, junk values included
+    rng = np.random.default_rng(100 + n)
+    recs = rng.integers(0, 9, size=(n, 64, 3), dtype=np.uint8)
+    assert np.array_equal(cab.encode_records(recs), port.encode_records(recs))
+
+
+def test_encoder_rejects_misaligned_device_buffers(cab):
+    import ctypes as C
+    with pytest.raises(cab.CabError):
+        cab._ck(cab.lib().cab_encode_dev(C.c_void_p(0x1008), 1, C.c_void_p(0x2000), None))
+
+
 def test_forward_66_cases_vs_reference_golden(net, golden):
     y = net.predict_batch(golden["case_codes"])
     assert rel_err(y, golden["case_forward"]).max() < RTOL
