@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "cab_internal.cuh"
+#include "encode_simd.cuh"
 #include "mlp_stream_kernel.cuh"
 
 namespace cab {
@@ -32,18 +33,9 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 // (/root/reference/src/chess/piece.cpp:103-105,145-147,179-181,260-262; type/colour tables piece.fwd.h:122-133,287-308).
 // HBM-bound byte kernel: 192 B in, 64 B out per board. A CTA takes 64 boards (12 KB of records): the records arrive
 // by three fully coalesced 16-byte loads per thread into shared memory, a thread then encodes 16 consecutive squares
-// (48 B from shared memory at a 12-word stride: conflict-free for 128-bit accesses) and stores one 16-byte word.
+// (48 B from shared memory at a 12-word stride: conflict-free for 128-bit accesses), four at a time in byte-parallel
+// form (encode_simd.cuh: the scalar rule was issue-bound), and stores one 16-byte word.
 constexpr int kEncThreads = 256;  // 16 squares per thread = 64 boards per CTA
-__device__ __forceinline__ int encode_square(uint32_t type, uint32_t color, uint32_t flag) {
-  // base code by type: none 0, king 1, queen 3, rook 4, knight 6, bishop 7, pawn 8; flag adds 1 for king/rook/pawn
-  int k = 0;
-  if (type >= 1 && type <= 6 && (color == 1 || color == 2)) {
-    k = (int) ((0x876431u >> (4 * (type - 1))) & 0xfu);  // nibbles: king 1, queen 3, rook 4, knight 6, bishop 7, pawn 8
-    if (flag != 0 && (type == 1 || type == 3 || type == 6)) k += 1;
-    if (color == 2) k = -k;
-  }
-  return k;
-}
 __global__ void __launch_bounds__(kEncThreads) encode_kernel(const uint4 *__restrict__ rec, long n_hex,
                                                               uint4 *__restrict__ codes) {
   __shared__ uint4 sh[3 * kEncThreads];
@@ -64,15 +56,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const uint4 *__rest
   }
   uint32_t o[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {  // four squares = 12 bytes = words 3q .. 3q+2
-    const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
-    const int k0 = encode_square(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
-    const int k1 = encode_square(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
-    const int k2 = encode_square((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
-    const int k3 = encode_square((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
-    o[q] = (uint32_t) (uint8_t) k0 | ((uint32_t) (uint8_t) k1 << 8) | ((uint32_t) (uint8_t) k2 << 16) |
-           ((uint32_t) (uint8_t) k3 << 24);
-  }
+  for (int q = 0; q < 4; ++q) o[q] = encode4(w[3 * q], w[3 * q + 1], w[3 * q + 2]);   // four squares = 12 bytes = words 3q .. 3q+2
   __stcs(codes + hex0 + threadIdx.x, make_uint4(o[0], o[1], o[2], o[3]));
 }
 
@@ -361,6 +345,8 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
   }
   if (reinterpret_cast<uintptr_t>(d_codes) & 1) { set_error("board codes must be 2-byte aligned"); return CAB_EINVAL; }
   const size_t smem = forward_smem_bytes(a.a_units, n_cons, geo.n_stages, net->stage_bytes);
+  // (one pass per CTA for a 4 096-board launch is deliberate: 2 / 4 passes per CTA with 6-16 streams measured 0.65 / 0.63 of
+  // the pipe against 0.68 — CTAs that start at different moments desynchronise the SMs' requests for the weight stream)
   const int grid = (int) std::min<long>(a.n_groups, (long) net->sm_count * geo.ctas_per_sm);
   static const bool prof_env = getenv("CAB_FWD_PROFILE") != nullptr;
   if (prof_env) {

@@ -5,8 +5,8 @@ import importlib, json, os, sys, threading, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 cab = importlib.import_module("chess-ai_b200")
-golden = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "golden.npz"))
-net = cab.Network.from_weights([64, 144, 225, 100, 1], golden["latest_weights"])
+weights = np.fromfile(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "latest_weights.f64"), dtype="<f8")
+net = cab.Network.from_weights([64, 144, 225, 100, 1], weights)
 moves = int(os.environ.get("MOVES", "10"))
 prec = int(os.environ.get("PRECISION", "0"))
 for G in [int(a) for a in sys.argv[1:]] or [1, 2, 4]:

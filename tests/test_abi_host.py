@@ -107,3 +107,13 @@ def test_network_storage_requires_a_network(cab):
     cab.NetworkStorage._current_network = None
     with pytest.raises(cab.CabError):
         cab.NetworkStorage.current_network()
+
+
+def test_encoder_byte_parallel_rule_matches_the_scalar_rule(tmp_path):
+    """csrc/encode_simd.cuh is host-compilable: all type / colour bytes (junk included) in all four square positions."""
+    import subprocess
+    exe = str(tmp_path / "encode_simd_check")
+    subprocess.check_call(["g++", "-O2", "-I", os.path.join(ROOT, "chess-ai_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "encode_simd_check.cpp"), "-o", exe])
+    out = subprocess.check_output([exe], timeout=120).decode()
+    assert " bad 0" in out, out
