@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libchessai_b200.so")
 SOURCES = ["cab_api.cu", "cab_train.cu", "cab_tc.cu", "cab_leafq.cu", "cab_prediction.cu", "cab_mcts.cu"]
-HEADERS = ["cab_internal.cuh", "chess_rules.cuh", "mlp_stream_kernel.cuh", "tc_gemm_bf16.cuh", "mlp_tc_fused.cuh", "train_kernels.cuh", os.path.join("..", "..", "include", "chessai_b200.h"),
+HEADERS = ["cab_internal.cuh", "chess_rules.cuh", "encode_simd.cuh", "mlp_stream_kernel.cuh", "tc_gemm_bf16.cuh", "mlp_tc_fused.cuh", "train_kernels.cuh", os.path.join("..", "..", "include", "chessai_b200.h"),
            os.path.join("..", "host", "fastchess.hpp")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

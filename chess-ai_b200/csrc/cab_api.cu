@@ -225,7 +225,7 @@ static void build_plan(const cab_net *net, bool transposed, StreamPlan *plan) {
 static int upload_plan(StreamPlan *plan) {
   if (plan->total_doubles == 0) return CAB_OK;
   CAB_CUDA(cudaMalloc(&plan->d_chunks, plan->chunks.size() * sizeof(ChunkDesc)));
-  CAB_CUDA(cudaMemcpy(plan->d_chunks, plan->chunks.data(), plan->chunks.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice));
+  CAB_CUDA(upload_now(plan->d_chunks, plan->chunks.data(), plan->chunks.size() * sizeof(ChunkDesc)));
   {  // the kernel's start-up tables in one piece: the first kSmemChunks descriptors, then the exp table (the device's own copy)
     std::vector<uint8_t> blob(kBlobBytes, 0);
     memcpy(blob.data(), plan->chunks.data(), std::min(plan->chunks.size(), (size_t) kSmemChunks) * sizeof(ChunkDesc));
@@ -233,10 +233,10 @@ static int upload_plan(StreamPlan *plan) {
     double *tbl8 = reinterpret_cast<double *>(blob.data() + kBlobChunkBytes);
     for (int j = 0; j < kExpTblSize; ++j) tbl8[j] *= 0.125;     // act_f_tbl wants T[j] / 8 (exact scaling)
     CAB_CUDA(cudaMalloc(&plan->d_blob, kBlobBytes));
-    CAB_CUDA(cudaMemcpy(plan->d_blob, blob.data(), kBlobBytes, cudaMemcpyHostToDevice));
+    CAB_CUDA(upload_now(plan->d_blob, blob.data(), kBlobBytes));
   }
   CAB_CUDA(cudaMalloc(&plan->d_segs, plan->segs.size() * sizeof(PackSeg)));
-  CAB_CUDA(cudaMemcpy(plan->d_segs, plan->segs.data(), plan->segs.size() * sizeof(PackSeg), cudaMemcpyHostToDevice));
+  CAB_CUDA(upload_now(plan->d_segs, plan->segs.data(), plan->segs.size() * sizeof(PackSeg)));
   CAB_CUDA(cudaMalloc(&plan->d_pack, plan->total_doubles * sizeof(double)));
   return CAB_OK;
 }
@@ -354,7 +354,7 @@ int launch_forward(cab_net *net, const int8_t *d_codes, long n_boards, double *d
     long long *d_prof = nullptr;
     const long nw = (long) grid * n_cons * 2;
     CAB_CUDA(cudaMalloc(&d_prof, nw * 8 * sizeof(long long)));
-    CAB_CUDA(cudaMemset(d_prof, 0, nw * 8 * sizeof(long long)));
+    CAB_CUDA(memset_now(d_prof, 0, nw * 8 * sizeof(long long)));
     a.prof = d_prof;
     CAB_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     mlp_forward_kernel<true><<<grid, n_cons * 64, smem, stream>>>(a);
@@ -426,7 +426,7 @@ static int init_net(cab_net *net, const std::vector<int> &dims, int device) {
   net->act_units_total = u;
   net->n_weights = w;
   CAB_CUDA(cudaMalloc(&net->d_w, w * sizeof(double)));
-  CAB_CUDA(cudaMemset(net->d_w, 0, w * sizeof(double)));
+  CAB_CUDA(memset_now(net->d_w, 0, w * sizeof(double)));
   build_plan(net, false, &net->fwd);
   build_plan(net, true, &net->bwd);
   if ((rc = upload_plan(&net->fwd)) != CAB_OK) return rc;
@@ -608,7 +608,7 @@ int cab_net_set_weights(cab_net *net, const double *w, long n) {
   int rc = select_device(net->device);
   if (rc != CAB_OK) return rc;
   CAB_CUDA(cudaDeviceSynchronize());
-  CAB_CUDA(cudaMemcpy(net->d_w, w, n * sizeof(double), cudaMemcpyHostToDevice));
+  CAB_CUDA(upload_now(net->d_w, w, n * sizeof(double)));
   net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   return CAB_OK;
 }
@@ -640,7 +640,7 @@ int cab_net_zero(cab_net *net) {
   int rc = select_device(net->device);
   if (rc != CAB_OK) return rc;
   CAB_CUDA(cudaDeviceSynchronize());
-  CAB_CUDA(cudaMemset(net->d_w, 0, net->n_weights * sizeof(double)));
+  CAB_CUDA(memset_now(net->d_w, 0, net->n_weights * sizeof(double)));
   net->pack_dirty = net->tc_dirty = net->f16_dirty = true;
   return CAB_OK;
 }
@@ -724,7 +724,7 @@ int cab_encode_host(int device, const uint8_t *records, long n, int8_t *codes) {
   int8_t *d_c = nullptr;
   CAB_CUDA(cudaMalloc(&d_r, n * 192));
   CAB_CUDA(cudaMalloc(&d_c, n * 64));
-  CAB_CUDA(cudaMemcpy(d_r, records, n * 192, cudaMemcpyHostToDevice));
+  CAB_CUDA(upload_now(d_r, records, n * 192));
   rc = cab_encode_dev(d_r, n, d_c, nullptr);
   if (rc == CAB_OK && cudaMemcpy(codes, d_c, n * 64, cudaMemcpyDeviceToHost) != cudaSuccess) rc = CAB_ECUDA;
   cudaFree(d_r); cudaFree(d_c);
@@ -791,12 +791,12 @@ static int forward_full_impl(cab_net *net, const int8_t *codes, long n, double *
   CAB_CUDA(cudaMalloc(&codes_b.p, n * 64));
   CAB_CUDA(cudaMalloc(&out_b.p, n * sizeof(double)));
   CAB_CUDA(cudaMalloc(&save_b.p, tensor * sizeof(double)));
-  CAB_CUDA(cudaMemset(save_b.p, 0, tensor * sizeof(double)));
+  CAB_CUDA(memset_now(save_b.p, 0, tensor * sizeof(double)));
   if (thetas_host != nullptr) {
     CAB_CUDA(cudaMalloc(&theta_b.p, tensor * sizeof(double)));
-    CAB_CUDA(cudaMemset(theta_b.p, 0, tensor * sizeof(double)));
+    CAB_CUDA(memset_now(theta_b.p, 0, tensor * sizeof(double)));
   }
-  CAB_CUDA(cudaMemcpy(codes_b.p, codes, n * 64, cudaMemcpyHostToDevice));
+  CAB_CUDA(upload_now(codes_b.p, codes, n * 64));
   {
     std::lock_guard<std::mutex> lk(net->mu);
     rc = ensure_packed(net, nullptr, true);

@@ -161,6 +161,23 @@ size_t forward_smem_bytes(int a_units, int n_cons, int n_stages, int stage_bytes
     if (e__ != cudaSuccess) return cab::cuda_fail(e__, #call, __FILE__, __LINE__); \
   } while (0)
 
+// cudaMemset of device memory on the legacy stream returns before the fill has run, and the library's own streams are
+// created cudaStreamNonBlocking: they do NOT wait for the legacy stream. A buffer zeroed at allocation and written right
+// after on such a stream (the trainer's lambda upload into d_scalars) could be zeroed AFTER the write (seen once in ~10
+// runs of lib/train on a slow box: lambda read as 0 -> reset rule -> dropout). Every set-up fill therefore completes here.
+inline cudaError_t memset_now(void *p, int value, size_t bytes) {
+  cudaError_t e = cudaMemset(p, value, bytes);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(cudaStreamLegacy);
+}
+
+// Likewise a synchronous cudaMemcpy from PAGEABLE host memory returns once the bytes sit in the driver's staging buffer;
+// the DMA to the device runs on the legacy stream. Set-up uploads (weights, plans, tables) complete here before any
+// non-blocking stream may read them.
+inline cudaError_t upload_now(void *dst, const void *src, size_t bytes) {
+  cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(cudaStreamLegacy);
+}
+
 // ---- device helpers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 

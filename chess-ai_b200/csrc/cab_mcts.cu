@@ -204,12 +204,13 @@ __device__ int warp_movegen(WarpShared *ws) {
     if (lane == 0) c = !crules::attacked(crules::plain(sq), ks >> 3, ks & 7, color);
     calm = __shfl_sync(0xffffffffu, c, 0) != 0;
   }
-  uint64_t m[2];
-#pragma unroll
+  uint64_t m[2] = {0ull, 0ull};
+#pragma unroll 1                                     // ONE inlined copy of the rules (instruction footprint), two trips
   for (int h = 0; h < 2; ++h) {
     const int from = lane + 32 * h;
     const int k = sq[from];
-    m[h] = (k != 0 && crules::color_of(k) == color) ? crules::legal_targets(sq, from, color, ks, calm) : 0ull;
+    const uint64_t mh = (k != 0 && crules::color_of(k) == color) ? crules::legal_targets(sq, from, color, ks, calm) : 0ull;
+    if (h == 0) m[0] = mh; else m[1] = mh;
   }
   const int c0 = __popcll(m[0]), c1 = __popcll(m[1]);
   int s0 = c0, s1 = c1;                              // inclusive prefix sums over the lanes
@@ -532,28 +533,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) mcts_walk_kernel(const Dev 
     __syncwarp();
     if (pl->slot >= 0) finish_expansion(d, res, tree, arena, pl->node, pl->slot, ws, game->moves_played);
   }
-  // (2) resume them in order; those that park again are compacted to the front
+  // (2) resume them in order; those that park again are compacted to the front. (3) then new playouts, one at a time
+  // until the root exists. One loop, so that advance() is inlined once (instruction footprint).
   int done = ts->done, launched = ts->launched, kept = 0;
   Walk p;
-  for (int i = 0; i < n_parked; ++i) {
-    unpark(d, tree, ws, p, i);
-    if (advance(d, tree, arena, ws, p)) ++done;
-    else park(d, tree, ws, p, kept++);
-  }
-  // (3) new playouts (one at a time until the root exists)
   int budget = d.max_launch;
-  while (kept < d.in_flight && launched < d.quota && budget-- > 0) {
-    if (!(arena[0].flags & kExpanded) && launched > done) break;
-    __syncwarp();
-    {
-      uint16_t *pd = reinterpret_cast<uint16_t *>(&ws->pos);
-      const uint16_t *ps = reinterpret_cast<const uint16_t *>(&game->pos);
-      for (int i = lane; i < (int) (sizeof(Pos) / 2); i += 32) pd[i] = ps[i];
-      if (lane == 0) ws->path[0] = 0;
+  for (int i = 0;;) {
+    if (i < n_parked) {
+      unpark(d, tree, ws, p, i++);
+    } else {
+      if (!(kept < d.in_flight && launched < d.quota && budget-- > 0)) break;
+      if (!(arena[0].flags & kExpanded) && launched > done) break;
+      __syncwarp();
+      {
+        uint16_t *pd = reinterpret_cast<uint16_t *>(&ws->pos);
+        const uint16_t *ps = reinterpret_cast<const uint16_t *>(&game->pos);
+        for (int w = lane; w < (int) (sizeof(Pos) / 2); w += 32) pd[w] = ps[w];
+        if (lane == 0) ws->path[0] = 0;
+      }
+      __syncwarp();
+      p.node = 0; p.depth = 0; p.path_len = 1; p.slot = -1;
+      ++launched;
     }
-    __syncwarp();
-    p.node = 0; p.depth = 0; p.path_len = 1; p.slot = -1;
-    ++launched;
     if (advance(d, tree, arena, ws, p)) ++done;
     else park(d, tree, ws, p, kept++);
   }
@@ -752,9 +753,9 @@ static int mcts_build(cab_mcts *q) {
   CAB_CUDA(cudaMalloc(&d.games, p.games * sizeof(GameState)));
   CAB_CUDA(cudaMalloc(&d.req, (size_t) trees * p.in_flight * sizeof(int)));
   CAB_CUDA(cudaMalloc(&d.req_count, sizeof(int)));
-  CAB_CUDA(cudaMemset(d.req_count, 0, sizeof(int)));
+  CAB_CUDA(memset_now(d.req_count, 0, sizeof(int)));
   CAB_CUDA(cudaMalloc(&d.cnt, sizeof(Counters)));
-  CAB_CUDA(cudaMemset(d.cnt, 0, sizeof(Counters)));
+  CAB_CUDA(memset_now(d.cnt, 0, sizeof(Counters)));
   d.cases_cap = p.save_ratio > 0.0 ? (int) std::min<long>((long) p.games * (p.max_moves + 1), 1L << 24) : 1;
   CAB_CUDA(cudaMalloc(&d.cases, (size_t) d.cases_cap * sizeof(KeptCase)));
   // one round queues at most trees * in_flight expansions; ~40 boards each when every child is evaluated
@@ -764,7 +765,7 @@ static int mcts_build(cab_mcts *q) {
     CAB_CUDA(cudaMalloc(&d.eval_codes[b], (size_t) d.eval_cap * 64));
     CAB_CUDA(cudaMalloc(&d.eval_out[b], (size_t) d.eval_cap * sizeof(double)));
     CAB_CUDA(cudaMalloc(&d.eval_count[b], sizeof(int)));
-    CAB_CUDA(cudaMemset(d.eval_count[b], 0, sizeof(int)));
+    CAB_CUDA(memset_now(d.eval_count[b], 0, sizeof(int)));
   }
   // tables from the host's libm: the very values the reference's search computes
   d.pf_n = d.quota * p.roots + p.in_flight * p.roots + 64;
@@ -773,8 +774,8 @@ static int mcts_build(cab_mcts *q) {
   for (int m = 0; m <= 2048; ++m) { const double value = (double) (m - 1024); sig[m] = 1.0 / (1.0 + std::exp(-value / 27.18)); }  // :252
   CAB_CUDA(cudaMalloc(&q->d_pf, pf.size() * sizeof(double)));
   CAB_CUDA(cudaMalloc(&q->d_sig, sig.size() * sizeof(double)));
-  CAB_CUDA(cudaMemcpy(q->d_pf, pf.data(), pf.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CAB_CUDA(cudaMemcpy(q->d_sig, sig.data(), sig.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CAB_CUDA(upload_now(q->d_pf, pf.data(), pf.size() * sizeof(double)));
+  CAB_CUDA(upload_now(q->d_sig, sig.data(), sig.size() * sizeof(double)));
   d.pf_tbl = q->d_pf; d.sig_tbl = q->d_sig;
   d.exp20 = std::exp(20.0);
   CAB_CUDA(cudaMallocHost(&q->h_count, sizeof(int)));
@@ -794,7 +795,7 @@ static int mcts_build(cab_mcts *q) {
     for (int c = 0; c < 8; ++c) { g.pos.sq[c] = back[c]; g.pos.sq[8 + c] = 8; g.pos.sq[48 + c] = -8; g.pos.sq[56 + c] = (int8_t) -back[c]; }
     g.pos.side = 1;
   }
-  CAB_CUDA(cudaMemcpy(d.games, gs.data(), gs.size() * sizeof(GameState), cudaMemcpyHostToDevice));
+  CAB_CUDA(upload_now(d.games, gs.data(), gs.size() * sizeof(GameState)));
   mcts_reset_kernel<<<(p.games + 127) / 128, 128, 0, q->stream>>>(d);
   CAB_CUDA(cudaGetLastError());
   CAB_CUDA(cudaStreamSynchronize(q->stream));
@@ -840,9 +841,9 @@ int cab_mcts_set_positions(cab_mcts *q, const int8_t *codes, const int8_t *side,
     gs[g].pos.side = side[g];
     gs[g].pos.no_capture = no_capture ? no_capture[g] : 0;
   }
-  CAB_CUDA(cudaMemcpy(q->d.games, gs.data(), gs.size() * sizeof(GameState), cudaMemcpyHostToDevice));
-  CAB_CUDA(cudaMemset(q->d.cnt, 0, sizeof(Counters)));
-  for (int b = 0; b < 2; ++b) CAB_CUDA(cudaMemset(q->d.eval_count[b], 0, sizeof(int)));
+  CAB_CUDA(upload_now(q->d.games, gs.data(), gs.size() * sizeof(GameState)));
+  CAB_CUDA(memset_now(q->d.cnt, 0, sizeof(Counters)));
+  for (int b = 0; b < 2; ++b) CAB_CUDA(memset_now(q->d.eval_count[b], 0, sizeof(int)));
   mcts_reset_kernel<<<(q->prm.games + 127) / 128, 128, 0, q->stream>>>(q->d);
   CAB_CUDA(cudaGetLastError());
   CAB_CUDA(cudaStreamSynchronize(q->stream));
@@ -1028,9 +1029,9 @@ int cab_movegen_host(int device, const int8_t *codes, const int8_t *side, int n,
   CAB_CUDA(cudaMalloc(&ds.p, n));
   CAB_CUDA(cudaMalloc(&dn.p, n * sizeof(int)));
   CAB_CUDA(cudaMalloc(&dm.p, (size_t) n * cap * 3));
-  if (no_reply_out) { CAB_CUDA(cudaMalloc(&df.p, (size_t) n * cap)); CAB_CUDA(cudaMemset(df.p, 0, (size_t) n * cap)); }
-  CAB_CUDA(cudaMemcpy(dc.p, codes, (size_t) n * 64, cudaMemcpyHostToDevice));
-  CAB_CUDA(cudaMemcpy(ds.p, side, n, cudaMemcpyHostToDevice));
+  if (no_reply_out) { CAB_CUDA(cudaMalloc(&df.p, (size_t) n * cap)); CAB_CUDA(memset_now(df.p, 0, (size_t) n * cap)); }
+  CAB_CUDA(upload_now(dc.p, codes, (size_t) n * 64));
+  CAB_CUDA(upload_now(ds.p, side, n));
   movegen_kernel<<<(n + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32>>>((const int8_t *) dc.p, (const int8_t *) ds.p, n, queen_only,
                                                                                 (int *) dn.p, (uint8_t *) dm.p, cap, (uint8_t *) df.p);
   CAB_CUDA(cudaGetLastError());

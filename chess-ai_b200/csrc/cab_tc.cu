@@ -195,7 +195,7 @@ static int f16_launch(cab_net *net, const int8_t *d_codes, long n, double *d_out
   long long *d_prof = nullptr;
   if (profile) {
     CAB_CUDA(cudaMalloc(&d_prof, (size_t) net->sm_count * 64 * sizeof(long long)));
-    CAB_CUDA(cudaMemset(d_prof, 0, (size_t) net->sm_count * 64 * sizeof(long long)));
+    CAB_CUDA(memset_now(d_prof, 0, (size_t) net->sm_count * 64 * sizeof(long long)));
     a.prof = d_prof;
   }
   static const int ch = getenv("CAB_F16_CH") ? atoi(getenv("CAB_F16_CH")) : 16;   // accumulator columns per epilogue chunk (sweeps: 16 is best)
@@ -411,11 +411,11 @@ static int tc_train_prepare(cab_net *net, long n, cudaStream_t stream) {
     for (int l = 0; l + 1 < L; ++l) {
       const size_t bytes = (size_t) ld * net->dims[l] * 2;
       CAB_CUDA(cudaMalloc(&s->a_rm[l], bytes));
-      if (l + 2 < L) { CAB_CUDA(cudaMalloc(&s->a_t[l], bytes)); CAB_CUDA(cudaMemset(s->a_t[l], 0, bytes)); }
+      if (l + 2 < L) { CAB_CUDA(cudaMalloc(&s->a_t[l], bytes)); CAB_CUDA(memset_now(s->a_t[l], 0, bytes)); }
       if (l >= 1) {
         CAB_CUDA(cudaMalloc(&s->p_rm[l], bytes));
         CAB_CUDA(cudaMalloc(&s->p_t[l], bytes));
-        CAB_CUDA(cudaMemset(s->p_t[l], 0, bytes));
+        CAB_CUDA(memset_now(s->p_t[l], 0, bytes));
       }
     }
     CAB_CUDA(cudaMalloc(&s->psi_out, ld * sizeof(float)));

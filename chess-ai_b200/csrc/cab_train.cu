@@ -74,19 +74,19 @@ static int ensure_train_state(cab_net *net) {
   if (net->train_stream == nullptr) CAB_CUDA(cudaStreamCreateWithFlags(&net->train_stream, cudaStreamNonBlocking));
   if (net->d_dw == nullptr) {
     CAB_CUDA(cudaMalloc(&net->d_dw, net->n_weights * sizeof(double)));
-    CAB_CUDA(cudaMemset(net->d_dw, 0, net->n_weights * sizeof(double)));
+    CAB_CUDA(memset_now(net->d_dw, 0, net->n_weights * sizeof(double)));
   }
   if (net->d_grad == nullptr) {
     CAB_CUDA(cudaMalloc(&net->d_grad, (net->n_weights + 4) * sizeof(double)));
-    CAB_CUDA(cudaMemset(net->d_grad, 0, (net->n_weights + 4) * sizeof(double)));
+    CAB_CUDA(memset_now(net->d_grad, 0, (net->n_weights + 4) * sizeof(double)));
   }
   if (net->d_scalars == nullptr) {
     CAB_CUDA(cudaMalloc(&net->d_scalars, 64 * sizeof(double)));
-    CAB_CUDA(cudaMemset(net->d_scalars, 0, 64 * sizeof(double)));
+    CAB_CUDA(memset_now(net->d_scalars, 0, 64 * sizeof(double)));
   }
   if (net->d_ctl == nullptr) {
     CAB_CUDA(cudaMalloc(&net->d_ctl, sizeof(TrainCtl)));
-    CAB_CUDA(cudaMemset(net->d_ctl, 0, sizeof(TrainCtl)));
+    CAB_CUDA(memset_now(net->d_ctl, 0, sizeof(TrainCtl)));
   }
   return CAB_OK;
 }
@@ -100,8 +100,8 @@ static int ensure_batch_buffers(cab_net *net, long n) {
     CAB_CUDA(cudaMalloc(&net->d_acts, bytes));
     CAB_CUDA(cudaMalloc(&net->d_psis, bytes));
     CAB_CUDA(cudaMalloc(&net->d_tout, pad * sizeof(double)));
-    CAB_CUDA(cudaMemset(net->d_acts, 0, bytes));
-    CAB_CUDA(cudaMemset(net->d_psis, 0, bytes));
+    CAB_CUDA(memset_now(net->d_acts, 0, bytes));
+    CAB_CUDA(memset_now(net->d_psis, 0, bytes));
     net->train_cap = pad;
   }
   return CAB_OK;
@@ -161,7 +161,7 @@ static int build_grad_items(cab_net *net, GradPlan &gp, long n) {
   cudaFree(gp.d_items);
   gp.d_items = nullptr;
   CAB_CUDA(cudaMalloc(&gp.d_items, items.size() * sizeof(GradItem)));
-  CAB_CUDA(cudaMemcpy(gp.d_items, items.data(), items.size() * sizeof(GradItem), cudaMemcpyHostToDevice));
+  CAB_CUDA(upload_now(gp.d_items, items.data(), items.size() * sizeof(GradItem)));
   gp.n_items = (int) items.size();
   gp.items_n = n;
   return CAB_OK;
@@ -199,7 +199,7 @@ static int get_grad_plan(cab_net *net, long n, GradPlan *out) {
   GradPlan gp;
   gp.n_tasks = (int) tasks.size();
   CAB_CUDA(cudaMalloc(&gp.d_tasks, tasks.size() * sizeof(GradTask)));
-  CAB_CUDA(cudaMemcpy(gp.d_tasks, tasks.data(), tasks.size() * sizeof(GradTask), cudaMemcpyHostToDevice));
+  CAB_CUDA(upload_now(gp.d_tasks, tasks.data(), tasks.size() * sizeof(GradTask)));
   gp.tasks = tasks;
   int rc = build_grad_items(net, gp, n);
   g_grad_plans.push_back({net, gp});
@@ -591,7 +591,7 @@ int cab_dp_peer_export(cab_net *net, void *handle64_out) {
     size_t og[2], oe, ofg, ofe;
     const size_t bytes = peer_block_bytes(net->n_weights, og, &oe, &ofg, &ofe);
     CAB_CUDA(cudaMalloc(&net->peer_block, bytes));
-    CAB_CUDA(cudaMemset(net->peer_block, 0, bytes));
+    CAB_CUDA(memset_now(net->peer_block, 0, bytes));
     CAB_CUDA(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t h;
@@ -618,7 +618,7 @@ int cab_dp_peer_attach(cab_net *net, const void *handles64, int rank, int world)
     net->peer_map[r] = p;
   }
   CAB_CUDA(cudaMalloc(&net->d_peer_table, kPeerMax * sizeof(void *)));
-  CAB_CUDA(cudaMemcpy(net->d_peer_table, net->peer_map, kPeerMax * sizeof(void *), cudaMemcpyHostToDevice));
+  CAB_CUDA(upload_now(net->d_peer_table, net->peer_map, kPeerMax * sizeof(void *)));
   net->d_grad_own = net->d_grad;
   net->dp_rank = rank;
   net->dp_world = world;
@@ -633,7 +633,7 @@ int cab_dropout(cab_net *net, double rate, uint64_t seed, uint64_t offset, long 
   CAB_CUDA(cudaDeviceSynchronize());
   unsigned long long *d_hits = nullptr;
   CAB_CUDA(cudaMalloc(&d_hits, sizeof(unsigned long long)));
-  CAB_CUDA(cudaMemset(d_hits, 0, sizeof(unsigned long long)));
+  CAB_CUDA(memset_now(d_hits, 0, sizeof(unsigned long long)));
   dropout_kernel<<<(int) std::min<long>((net->n_weights + 255) / 256, 148L * 8), 256>>>(net->d_w, net->n_weights, rate,
                                                                                           seed, offset, d_hits);
   net->launches++;

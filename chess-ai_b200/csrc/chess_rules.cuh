@@ -49,6 +49,7 @@ CR_HD View plain(const int8_t *sq) { return View{sq, -1, -1, 0}; }
 // Board::getPositionThreats (game.cpp:66-174) > 0 for the square (r, c) of a piece of colour king_color
 CR_HD bool attacked(const View &v, int r, int c, int king_color) {
   const int enemy = -king_color;
+#pragma unroll 1
   for (int d = 0; d < 8; ++d) {   // 0-3 rank / file, 4-7 diagonals
     const int dr = d < 4 ? (d == 0) - (d == 1) : ((d & 2) ? -1 : 1);
     const int dc = d < 4 ? (d == 2) - (d == 3) : ((d & 1) ? -1 : 1);
@@ -63,12 +64,18 @@ CR_HD bool attacked(const View &v, int r, int c, int king_color) {
       x += dr; y += dc;
     }
   }
+  // (the short loops below stay rolled on the device: this function is inlined several times per kernel and the search
+  // kernels are bound by instruction fetch, not by these few iterations)
+#pragma unroll 1
   for (int x = r - 1; x <= r + 1; ++x)
+#pragma unroll 1
     for (int y = c - 1; y <= c + 1; ++y)
       if (on_board(x, y)) { const int k = v.at(x * 8 + y); if (color_of(k) == enemy && kind_of(k) == 1) return true; }
   const int px = r + (enemy > 0 ? -1 : 1);  // a white pawn attacks from below, a black one from above
+#pragma unroll 1
   for (int dc = -1; dc <= 1; dc += 2)
     if (on_board(px, c + dc)) { const int k = v.at(px * 8 + c + dc); if (color_of(k) == enemy && kind_of(k) == 6) return true; }
+#pragma unroll 1
   for (int i = 0; i < 8; ++i) {   // knight jumps (+-1, +-2), (+-2, +-1)
     const int a = (i & 4) ? 2 : 1, b = 3 - a;
     const int x = r + ((i & 1) ? -a : a), y = c + ((i & 2) ? -b : b);
@@ -114,14 +121,20 @@ CR_HD uint64_t targets(const int8_t *sq, int from) {
           m |= 1ull << ((r1 + dr) * 8 + c1 + dc);
     if (iabs(k) == 1) {     // unmoved: castling
       const View v = plain(sq);
+      // rolled loops: ONE inlined copy of attacked() here instead of six (the walk / expand kernels starve on
+      // instruction fetch: ncu "no_instruction" 2.6 / 12.5 warps per issue)
+#pragma unroll 1
       for (int dir = -1; dir <= 1; dir += 2) {
         const int c2 = c1 + 2 * dir, rook_col = dir > 0 ? 7 : 0, mid = c1 + dir;
         if (!on_board(r1, c2)) continue;
         const int rk = sq[r1 * 8 + rook_col];
         if (!(kind_of(rk) == 3 && color_of(rk) == color && iabs(rk) == 4)) continue;   // own, unmoved rook
         if (color_of(sq[r1 * 8 + c2]) == color) continue;                               // Move::verify
-        if (attacked(v, r1, c1, color) || attacked(v, r1, c2, color)) continue;
-        if (sq[r1 * 8 + mid] != 0 || attacked(v, r1, mid, color)) continue;
+        if (sq[r1 * 8 + mid] != 0) continue;
+        bool hit = false;                                                               // king, middle and target square unattacked
+#pragma unroll 1
+        for (int j = 0; j < 3 && !hit; ++j) hit = attacked(v, r1, c1 + j * dir, color);
+        if (hit) continue;
         m |= 1ull << (r1 * 8 + c2);
       }
     }
