@@ -107,6 +107,7 @@ struct WarpShared {
   int path[kDepth + 2];
   uint16_t moves[kMaxChildren];                 // from | to << 8 of the expansion under construction
   uint32_t eval_mask[kMaxChildren / 32];        // children whose board goes to the network
+  int8_t base[64];                              // the parent with every moved2x flag cleared: what each child starts from
   int8_t child[32 * kBoardStride];              // one scratch board per lane
   double weight[kMaxChildren];                  // exp(cm * logit) per child while the priors are formed
 };
@@ -155,18 +156,33 @@ __device__ int select_child(const Dev &d, const Node *arena, const Node &n) {
     const double s = puct_score(pf, sq, arena[n.first_child + i]);
     if (s > best_s) { best_s = s; best_i = i; }
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    const double os = __shfl_xor_sync(0xffffffffu, best_s, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-    if (oi >= 0 && (best_i < 0 || os > best_s || (os == best_s && oi < best_i))) { best_s = os; best_i = oi; }
-  }
-  return best_i < 0 ? -1 : n.first_child + best_i;
+  // warp argmax with "first wins": scores are >= +0.0 (prior, value and the exploration factor are non-negative), so their
+  // bit patterns order like unsigned integers: two 32-bit max reductions (REDUX) find the greatest score, a min reduction
+  // the smallest child index that has it (five shuffle rounds of a double + an index before)
+  if (n.n_children == 0) return -1;
+  const unsigned long long key = best_i >= 0 ? (unsigned long long) __double_as_longlong(best_s) : 0ull;
+  const unsigned hi = (unsigned) (key >> 32), lo = (unsigned) key;
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  const bool top = best_i >= 0 && hi == mhi && lo == mlo;
+  const unsigned first = __reduce_min_sync(0xffffffffu, top ? (unsigned) best_i : 0x7fffffffu);
+  return first == 0x7fffffffu ? -1 : n.first_child + (int) first;
 }
 
 // Game::tryMove without the mate / stalemate scan (game.cpp:847-871); that scan's outcome is cached in Node::state
 __device__ void play_lazy(Pos *pos, int from, int to, int promo) {
+  {   // every moved2x flag falls (game.cpp:505-513): two squares per lane instead of 64 trips of one lane
+    const int lane = lane_id();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int8_t v = pos->sq[lane + 32 * h];
+      if (v == 9) pos->sq[lane + 32 * h] = 8;
+      else if (v == -9) pos->sq[lane + 32 * h] = -8;
+    }
+    __syncwarp();
+  }
   if (lane_id() == 0) {
-    const bool capture = crules::apply_move(pos->sq, from, to, promo);
+    const bool capture = crules::apply_move_cleared(pos->sq, from, to, promo);
     pos->side = (int8_t) -pos->side;
     pos->no_capture = capture ? 0 : pos->no_capture + 1;
     if (pos->no_capture >= 50) { pos->over = 1; pos->result = 0; }
@@ -240,14 +256,25 @@ __device__ __forceinline__ bool promotes(const int8_t *sq, int from, int to) {
 
 // lane-private child board: the parent with move i made; a promotion becomes the BISHOP's, whose logit is the one the
 // reference's std::map keeps for the key (actionMap[move] = ..., decider.cpp:52-56)
+// Move::doMove first drops every moved2x flag (game.cpp:505-513) whatever the move: done ONCE per parent, two squares per
+// lane, instead of 64 trips per child. Call after warp_movegen (en passant needs the flags) and before make_child.
+__device__ __forceinline__ void prepare_children(WarpShared *ws) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int8_t v = ws->pos.sq[lane + 32 * h];
+    ws->base[lane + 32 * h] = v == 9 ? (int8_t) 8 : (v == -9 ? (int8_t) -8 : v);
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ int8_t *make_child(WarpShared *ws, int i) {
   int8_t *cb = ws->child + lane_id() * kBoardStride;
-  const uint32_t *src = reinterpret_cast<const uint32_t *>(ws->pos.sq);
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(ws->base);
   uint32_t *dst = reinterpret_cast<uint32_t *>(cb);
 #pragma unroll
   for (int w = 0; w < 16; ++w) dst[w] = src[w];
   const int from = ws->moves[i] & 0xff, to = ws->moves[i] >> 8;
-  crules::apply_move(cb, from, to, promotes(ws->pos.sq, from, to) ? 7 : 0);
+  crules::apply_move_cleared(cb, from, to, promotes(ws->pos.sq, from, to) ? 7 : 0);
   return cb;
 }
 
@@ -276,6 +303,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) mcts_expand_kernel(const De
   __syncwarp();
   Node &parent = arena[node];
   const int n = warp_movegen(ws);
+  prepare_children(ws);
   if (n <= 0) {                          // Game::updateGameState (game.cpp:872-890): stalemate if the king is safe, else lost
     if (lane == 0) {
       const int ks = crules::king_square(ws->pos.sq, ws->pos.side);
@@ -421,9 +449,12 @@ __device__ bool advance(const Dev &d, int tree, Node *arena, WarpShared *ws, Wal
   const int lane = lane_id();
   Pos *pos = &ws->pos;
   bool truncated = false;
+  // The node in hand is read ONCE into registers (one 40-byte round trip to L2 / HBM instead of one per field between the
+  // warp barriers); the chosen child's read serves the move to play and is the next iteration's node. Nobody else writes
+  // this tree (one warp per tree), and this playout writes only where it parks.
+  Node n = arena[p.node];
   while (p.depth < kDepth) {
     if (pos->over) break;
-    Node &n = arena[p.node];
     if (n.state == 2) {
       if (lane == 0) { pos->over = 1; pos->result = n.result; }
       __syncwarp();
@@ -433,7 +464,7 @@ __device__ bool advance(const Dev &d, int tree, Node *arena, WarpShared *ws, Wal
     if (!(n.flags & kExpanded)) {
       p.slot = -1;
       if (!(n.flags & kPending)) {     // the first playout to get here asks for the expansion (slot -2), later ones just wait
-        if (lane == 0) n.flags |= kPending;
+        if (lane == 0) arena[p.node].flags = (uint8_t) (n.flags | kPending);
         p.slot = -2;
       }
       if (lane < p.path_len) { Node &v = arena[ws->path[lane]]; v.visits += 1; v.vloss += 1; }   // virtual loss on the path
@@ -442,8 +473,8 @@ __device__ bool advance(const Dev &d, int tree, Node *arena, WarpShared *ws, Wal
     }
     const int best = select_child(d, arena, n);
     if (best < 0) break;
-    const Node &c = arena[best];
-    play_lazy(pos, c.from, c.to, c.promo);
+    n = arena[best];
+    play_lazy(pos, n.from, n.to, n.promo);
     p.node = best;
     if (lane == 0) ws->path[p.path_len] = best;
     ++p.path_len;
@@ -679,6 +710,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) movegen_kernel(const int8_t
   if (lane == 0) { ws->pos.side = side[p]; ws->pos.over = 0; ws->pos.result = 0; ws->pos.no_capture = 0; }
   __syncwarp();
   const int k = warp_movegen(ws);
+  prepare_children(ws);
   // expand promotions to Q R N B unless queen_only (game.cpp:404-417)
   int total = 0;
   if (lane == 0) {

@@ -214,11 +214,16 @@ CR_HD bool has_legal_move(const int8_t *sq, int color) {
 
 // Move::doMove (game.cpp:499-623) on the codes; promo = code base of the new piece (3 Q, 4 R, 6 N, 7 B) or 0.
 // Returns true when a piece was captured.
+// apply_move after the moved2x flags have been cleared (the MCTS walk clears them with all lanes of the warp)
+CR_HD bool apply_move_cleared(int8_t *sq, int from, int to, int promo);
 CR_HD bool apply_move(int8_t *sq, int from, int to, int promo) {
   for (int i = 0; i < 64; ++i) {                      // every moved2x flag falls (game.cpp:505-513)
     if (sq[i] == 9) sq[i] = 8;
     else if (sq[i] == -9) sq[i] = -8;
   }
+  return apply_move_cleared(sq, from, to, promo);
+}
+CR_HD bool apply_move_cleared(int8_t *sq, int from, int to, int promo) {
   const int r1 = from >> 3, c1 = from & 7, r2 = to >> 3, c2 = to & 7;
   const int k = sq[from], color = color_of(k), kind = kind_of(k);
   bool capture = sq[to] != 0;

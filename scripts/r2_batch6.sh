@@ -1,0 +1,6 @@
+#!/bin/bash
+out=gpurun_out
+python scripts/r2_walk_target.py > $out/r2_walk_plain.log 2>&1; echo plain rc=$?
+ncu --set full --clock-control none -k regex:'mcts_walk|mcts_expand|mcts_game' -s 60 -c 6 -o $out/r2_walk2 python scripts/r2_walk_target.py > $out/r2_walk2_ncu.log 2>&1; echo ncu rc=$?
+ncu -i $out/r2_walk2.ncu-rep --page raw --csv > $out/r2_walk2_raw.csv 2>/dev/null
+rm -f $out/r2_walk2.ncu-rep
