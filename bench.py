@@ -495,6 +495,34 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    # ---- K0 encoder (Network::loadBoard's integer stage): HBM-bound byte kernel, 192 B in + 64 B out per board ------------
+    encoder = None
+    try:
+        hbm_peak, hbm_src = 6539.2, "fallback (the pool's recorded copy bandwidth)"
+        ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(ppath):
+            hbm_peak, hbm_src = float(json.load(open(ppath)).get("hbm_gbs", hbm_peak)), "MEASURED_PEAKS.json hbm_gbs (copy, read+write bytes)"
+        n_enc = 1 << 21                                     # 384 MiB of records + 128 MiB of codes: larger than L2
+        recs = torch.randint(0, 7, (n_enc, 64, 3), dtype=torch.uint8, device="cuda")
+        enc_out = torch.empty(n_enc, 64, dtype=torch.int8, device="cuda")
+        L = cab.lib()
+        for _ in range(3):
+            cab._ck(L.cab_encode_dev(recs.data_ptr(), n_enc, enc_out.data_ptr(), stream_ptrs[0]))
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(streams[0])
+        for _ in range(10):
+            cab._ck(L.cab_encode_dev(recs.data_ptr(), n_enc, enc_out.data_ptr(), stream_ptrs[0]))
+        k1.record(streams[0])
+        torch.cuda.synchronize()
+        enc_s = k0.elapsed_time(k1) * 1e-3 / 10
+        encoder = {"kernel": "encode_kernel", "bound": "hbm", "boards_per_launch": n_enc, "bytes_per_board": 256,
+                   "launch_us": enc_s * 1e6, "achieved": 256 * n_enc / enc_s * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": 256 * n_enc / enc_s * 1e-9 / hbm_peak, "peak_source": hbm_src, "boards_per_s": n_enc / enc_s}
+        del recs, enc_out
+    except Exception as exc:
+        encoder = {"error": str(exc)}
+
     # ---- configs[4]: widened MLP on the bf16 tcgen05 path (N = 1 runs only) ---------------------------------------------
     wide = None
     if not args.no_wide and world == 1:
@@ -536,34 +564,6 @@ def main():
             del wnet
         except Exception as exc:
             wide = {"error": str(exc)}
-
-    # ---- K0 encoder (Network::loadBoard's integer stage): HBM-bound byte kernel, 192 B in + 64 B out per board ------------
-    encoder = None
-    try:
-        hbm_peak, hbm_src = 6539.2, "fallback (the pool's recorded copy bandwidth)"
-        ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(ppath):
-            hbm_peak, hbm_src = float(json.load(open(ppath)).get("hbm_gbs", hbm_peak)), "MEASURED_PEAKS.json hbm_gbs (copy, read+write bytes)"
-        n_enc = 1 << 21                                     # 384 MiB of records + 128 MiB of codes: larger than L2
-        recs = torch.randint(0, 7, (n_enc, 64, 3), dtype=torch.uint8, device="cuda")
-        enc_out = torch.empty(n_enc, 64, dtype=torch.int8, device="cuda")
-        L = cab.lib()
-        for _ in range(3):
-            cab._ck(L.cab_encode_dev(recs.data_ptr(), n_enc, enc_out.data_ptr(), stream_ptrs[0]))
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record(streams[0])
-        for _ in range(10):
-            cab._ck(L.cab_encode_dev(recs.data_ptr(), n_enc, enc_out.data_ptr(), stream_ptrs[0]))
-        k1.record(streams[0])
-        torch.cuda.synchronize()
-        enc_s = k0.elapsed_time(k1) * 1e-3 / 10
-        encoder = {"kernel": "encode_kernel", "bound": "hbm", "boards_per_launch": n_enc, "bytes_per_board": 256,
-                   "launch_us": enc_s * 1e6, "achieved": 256 * n_enc / enc_s * 1e-9, "peak": hbm_peak, "unit": "GB/s",
-                   "frac": 256 * n_enc / enc_s * 1e-9 / hbm_peak, "peak_source": hbm_src, "boards_per_s": n_enc / enc_s}
-        del recs, enc_out
-    except Exception as exc:
-        encoder = {"error": str(exc)}
 
     # ---- roofline of the dominant kernel (mlp_forward_kernel) on the fp64 tensor pipe -------------------------------
     n_fwd_launches = args.steps * (N_BOARDS // BATCH)
