@@ -1,5 +1,7 @@
 #!/bin/bash
-# passes per CTA of overlapping 4 096-board forward launches (CAB_FWD_PASSES) x streams: bench.py's eval legs only
+# passes per CTA of overlapping 4 096-board forward launches x streams: bench.py's eval legs only. RECORD of an experiment:
+# the CAB_FWD_PASSES knob it drove was removed again (launch_forward, cab_api.cu: one pass per CTA measured best,
+# profiles/r2_fwd_passes.jsonl); with the shipped library every line of this sweep is the 1-pass geometry.
 out=gpurun_out
 : > $out/r2_fwd_passes.jsonl
 run() { # passes streams
