@@ -203,9 +203,15 @@ __device__ void mark_over(Pos *pos, Node *n) {
   __syncwarp();
 }
 
-// legal moves of the side to move, from-squares over the lanes: lane l owns squares l and l + 32. Fills ws->moves in
-// the reference's order (from ascending, to ascending; one entry per (from, to): the std::map<Move> key, Q8) and
-// returns the count (warp-uniform).
+// legal moves of the side to move. Fills ws->moves in the reference's order (from ascending, to ascending; one entry per
+// (from, to): the std::map<Move> key, Q8) and returns the count (warp-uniform).
+//   (1) pseudo-legal targets with the from-squares over the lanes: lane l owns squares l and l + 32;
+//   (2) the (from, to) pairs whose legality needs canPieceMove's simulation (game.cpp:196-226: is the own king attacked
+//       with the piece lifted onto `to`?) are flattened into one list and dealt out one PAIR per lane — a queen's twenty
+//       simulations no longer run on one lane while thirty-one wait (the per-piece form kept 6.7 lanes busy per
+//       instruction in the expand kernel); the verdicts come back as bits OR-ed into per-square masks in shared memory.
+// Scratch: the pair list lives in ws->weight (free outside finish_expansion), the masks in ws->child (free until
+// make_child); <= 16 pieces x 27 targets = 432 pairs, the list holds 1 024.
 __device__ int warp_movegen(WarpShared *ws) {
   const int lane = lane_id();
   const int8_t *sq = ws->pos.sq;
@@ -220,13 +226,52 @@ __device__ int warp_movegen(WarpShared *ws) {
     if (lane == 0) c = !crules::attacked(crules::plain(sq), ks >> 3, ks & 7, color);
     calm = __shfl_sync(0xffffffffu, c, 0) != 0;
   }
+  uint16_t *pairs = reinterpret_cast<uint16_t *>(ws->weight);
+  uint32_t *mask = reinterpret_cast<uint32_t *>(ws->child);   // [64][2]: low / high half of a from-square's legal targets
   uint64_t m[2] = {0ull, 0ull};
+  bool sim[2] = {false, false};
 #pragma unroll 1                                     // ONE inlined copy of the rules (instruction footprint), two trips
   for (int h = 0; h < 2; ++h) {
     const int from = lane + 32 * h;
     const int k = sq[from];
-    const uint64_t mh = (k != 0 && crules::color_of(k) == color) ? crules::legal_targets(sq, from, color, ks, calm) : 0ull;
-    if (h == 0) m[0] = mh; else m[1] = mh;
+    const bool own = k != 0 && crules::color_of(k) == color;
+    const uint64_t mh = own ? crules::targets(sq, from) : 0ull;
+    // a non-king piece that shares no line with a calm king cannot uncover an attack (chess_rules.cuh legal_targets)
+    const bool sh = mh != 0 && ks >= 0 && !(calm && crules::kind_of(k) != 1 && !crules::aligned(from, ks));
+    mask[2 * from] = 0u; mask[2 * from + 1] = 0u;
+    if (h == 0) { m[0] = mh; sim[0] = sh; } else { m[1] = mh; sim[1] = sh; }
+  }
+  {
+    const int p0 = sim[0] ? __popcll(m[0]) : 0, p1 = sim[1] ? __popcll(m[1]) : 0;
+    int q = p0 + p1;                                 // this lane's pairs; exclusive prefix over the lanes
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, q, o);
+      if (lane >= o) q += t;
+    }
+    const int n_pairs = __shfl_sync(0xffffffffu, q, 31);
+    int at = q - p0 - p1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint64_t mm = sim[h] ? m[h] : 0ull;
+      while (mm) {
+        const int to = __ffsll((long long) mm) - 1;
+        mm &= mm - 1;
+        pairs[at++] = (uint16_t) ((lane + 32 * h) | (to << 8));
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < n_pairs; i += 32) {       // Board::canPieceMove for one (from, to) per lane
+      const int from = pairs[i] & 0xff, to = pairs[i] >> 8;
+      const int piece = sq[from];
+      const crules::View v{sq, from, to, piece};
+      const int k2 = crules::kind_of(piece) == 1 ? to : ks;   // a king move is tried with the king on `to`
+      if (!crules::attacked(v, k2 >> 3, k2 & 7, color)) atomicOr(&mask[2 * from + (to >> 5)], 1u << (to & 31));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (sim[h]) m[h] = ((uint64_t) mask[2 * (lane + 32 * h) + 1] << 32) | mask[2 * (lane + 32 * h)];
+    __syncwarp();                                    // the scratch is free again (make_child writes ws->child)
   }
   const int c0 = __popcll(m[0]), c1 = __popcll(m[1]);
   int s0 = c0, s1 = c1;                              // inclusive prefix sums over the lanes
