@@ -9,8 +9,10 @@ weights = np.fromfile(os.path.join(os.path.dirname(os.path.dirname(os.path.abspa
 net = cab.Network.from_weights([64, 144, 225, 100, 1], weights)
 moves = int(os.environ.get("MOVES", "10"))
 prec = int(os.environ.get("PRECISION", "0"))
+roots = int(os.environ.get("ROOTS", "8"))
+infl = int(os.environ.get("IN_FLIGHT", "16"))
 for G in [int(a) for a in sys.argv[1:]] or [1, 2, 4]:
-    sps = [cab.SelfPlay(net, games=512 // G, playouts_per_move=800, roots=8, in_flight=16, max_moves=moves, network_priors=1, noise=1,
+    sps = [cab.SelfPlay(net, games=512 // G, playouts_per_move=800, roots=roots, in_flight=infl, max_moves=moves, network_priors=1, noise=1,
                         save_ratio=0.1, seed=1234 + 1000 * g, precision=prec) for g in range(G)]
     stats = [None] * G
     def work(g):
@@ -21,7 +23,7 @@ for G in [int(a) for a in sys.argv[1:]] or [1, 2, 4]:
     for t in ths: t.join()
     secs = time.perf_counter() - t0
     tot = lambda k: sum(s[k] for s in stats)
-    print(json.dumps({"groups": G, "games": 512, "moves": moves, "precision": prec, "seconds": secs, "playouts_per_s": tot("playouts") / secs,
+    print(json.dumps({"groups": G, "games": 512, "moves": moves, "precision": prec, "roots": roots, "in_flight": infl, "seconds": secs, "playouts_per_s": tot("playouts") / secs,
                       "positions_per_s": tot("boards_evaluated") / secs, "moves_played": tot("moves_played"),
                       "evaluator_seconds_sum": tot("evaluator_seconds"), "rounds": [s["rounds"] for s in stats],
                       "eval_full": tot("eval_full"), "arena_full": tot("arena_full")}), flush=True)
