@@ -249,6 +249,7 @@ __device__ int warp_movegen(WarpShared *ws) {
       if (lane >= o) q += t;
     }
     const int n_pairs = __shfl_sync(0xffffffffu, q, 31);
+    if (n_pairs > (int) (sizeof(ws->weight) / sizeof(uint16_t))) return -1;   // not a chess position (dozens of queens): the list holds 1 024
     int at = q - p0 - p1;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
